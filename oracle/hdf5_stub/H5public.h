@@ -1,0 +1,1 @@
+#include "hdf5.h"
