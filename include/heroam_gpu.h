@@ -1,0 +1,184 @@
+/*
+ * include/heroam_gpu.h -- C ABI of libheroam_gpu.so, the B200 (sm_100a) engine for
+ * the Monte Carlo hot path of s-kesh/Sphere_roaming.
+ *
+ * The reference has no plugin registry; its seam is the C interface of
+ * src/simulation.h, called from exactly one place, simulate_for_number
+ * (src/main.c:50-97).  The entry points below are the batch forms of those
+ * calls.  Every function returns 0 on success and a non-zero HEROAM_E_* code on
+ * failure; heroam_gpu_last_error() then holds a message.  There is NO CPU
+ * fallback: without a usable CUDA device heroam_gpu_create fails.
+ *
+ *   reference call (file:line)                         replaced by
+ *   -------------------------------------------------  ------------------------------
+ *   initialize_particles      simulation.h:76-79,      heroam_gpu_sample_batch /
+ *                             simulation.c:277-337       heroam_gpu_sample_flat
+ *   #pragma omp parallel for                           heroam_gpu_simulate_batch /
+ *     simulate_particles      main.c:76-78,              heroam_gpu_simulate_flat
+ *                             simulation.h:94-97,
+ *                             simulation.c:438-526
+ *   free_particles            simulation.h:85,         heroam_gpu_free_particles
+ *                             simulation.c:339-341
+ *   (none: the reference leaves histogramming to       heroam_gpu_run_stats
+ *    the user of particlefile_after_<N>)
+ */
+#ifndef HEROAM_GPU_H_
+#define HEROAM_GPU_H_
+
+#include "heroam_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEROAM_ABI_VERSION 1
+
+enum {
+  HEROAM_OK = 0,
+  HEROAM_E_CUDA = 1,      /* CUDA runtime / driver failure (no device, launch error, OOM)   */
+  HEROAM_E_ARG = 2,       /* invalid argument or configuration                              */
+  HEROAM_E_UNSUPPORTED = 3, /* a trajectory has more particles than the kernels support      */
+  HEROAM_E_CLOCK = 4      /* dt/max_time such that the reference's float clock would stall
+                             and its loop never end                          */
+};
+
+/* Arithmetic mode of the integrator. */
+enum {
+  /* Every float operation of the reference in the reference's order, no FMA
+   * contraction, correctly rounded sqrt/divide, the one double-precision expression
+   * (simulation.c:220) in double: agrees bit-for-bit with the reference compiled
+   * `-O2 -ffp-contract=off`. */
+  HEROAM_MODE_EXACT = 0,
+  /* Same integrator and state, algebraically simplified (closed-form q (0,0,1) q^-1,
+   * dead zero-terms dropped), FMA contraction, hardware rsqrt: the counterpart of the
+   * reference's own `-O3 -ffast-math -march=native` release build.  Agrees with the
+   * strict reference within the tolerance stated in tests/test_gpu_parity.py. */
+  HEROAM_MODE_FAST = 1
+};
+
+/* How a trajectory left the step loop (heroam_traj_result.status). */
+enum {
+  HEROAM_DONE_SUCCESS = 0,  /* find_success criterion met (simulation.c:33-46, :519)       */
+  HEROAM_DONE_MAXTIME = 1,  /* time >= max_time (simulation.c:469)                         */
+  HEROAM_DONE_DEADLOCK = 2, /* no particle left to move, criterion unmet: the reference
+                               would never return; defined exit              */
+  HEROAM_DONE_STEPCAP = 4,  /* heroam_options.max_steps reached                            */
+  HEROAM_DONE_UNSUPPORTED = 6 /* more than 128 particles still moving: not integrated; the
+                               call returns HEROAM_E_UNSUPPORTED                            */
+};
+
+typedef struct heroam_options {
+  int mode;               /* HEROAM_MODE_*                                                 */
+  unsigned int segment_steps; /* steps a trajectory runs between re-binning passes (0 = default) */
+  unsigned long long max_steps; /* per-trajectory cap on loop iterations (0 = none)         */
+  int wide_kernel;        /* 0 = warp-per-trajectory kernel for > 8 moving particles (default);
+                             1 = the slow record-resident kernel (cross-check only)        */
+  int reserved[3];
+} heroam_options;
+
+typedef struct heroam_traj_result {
+  uint32_t steps;         /* iterations of the step loop                                   */
+  uint32_t status;        /* HEROAM_DONE_*                                                 */
+  uint32_t n_flagged;     /* particles with success == 1 at exit                           */
+  float time;             /* the loop's time variable at exit [fs]                         */
+} heroam_traj_result;
+
+/* Work and timing of the last simulate/run call on a context. */
+typedef struct heroam_run_info {
+  unsigned long long trajectories;
+  unsigned long long particles;
+  unsigned long long particle_steps; /* sum over steps of particles advanced               */
+  unsigned long long pair_steps;     /* sum over steps of active pairs a(a-1)/2            */
+  unsigned long long inrange_steps;  /* ... of which hit the force table                   */
+  unsigned long long passes;         /* re-binning passes                                  */
+  unsigned long long kernel_launches;/* kernels of this library launched                   */
+  double device_ms;       /* CUDA-event time, first kernel to last kernel (state resident) */
+  double integrate_ms;    /* sum of CUDA-event times of the integrate kernels alone        */
+  double h2d_ms, d2h_ms;  /* CUDA-event times of the copies (0 for resident runs)          */
+  unsigned long long h2d_bytes, d2h_bytes;
+} heroam_run_info;
+
+#define HEROAM_HIST_N 256
+#define HEROAM_HIST_T 4096
+typedef struct heroam_stats {
+  unsigned long long trajectories;
+  unsigned long long particles;
+  unsigned long long hist_n[HEROAM_HIST_N];   /* excitation count per trajectory (clamped) */
+  unsigned long long hist_traj_time[HEROAM_HIST_T]; /* loop time at exit, bins of max_time/4096 */
+  unsigned long long hist_meet_time[HEROAM_HIST_T]; /* per frozen particle: its time        */
+  unsigned long long done[8];                 /* trajectories by HEROAM_DONE_* code        */
+  unsigned long long unmet_particles;         /* particles still unpaired at exit          */
+  double sum_traj_time;                       /* sum of loop times at exit [fs]            */
+  heroam_run_info info;
+} heroam_stats;
+
+typedef struct heroam_ctx heroam_ctx;
+
+/* Library / device discovery.  heroam_gpu_device_count returns 0 without a GPU. */
+int heroam_gpu_abi_version(void);
+int heroam_gpu_device_count(void);
+const char *heroam_gpu_last_error(void);
+
+/* Context: one per GPU.  Uploads the force table (conf->force_grid_length floats,
+ * main.c:130) once; conf and force_list are copied, the caller may free them. */
+int heroam_gpu_create(const heroam_config *conf, const float *force_list, int device,
+                      const heroam_options *opt /* NULL = defaults (exact mode) */,
+                      heroam_ctx **out);
+void heroam_gpu_destroy(heroam_ctx *ctx);
+int heroam_gpu_set_mode(heroam_ctx *ctx, int mode);
+
+/* Drop-in for the loop at main.c:76-78.  Consumes host initial states in the
+ * reference's own Particles layout (from initialize_particles or from
+ * heroam_gpu_sample_batch) and writes the final states back in place; afterwards
+ * save_particles / particlefile_after_<N> work unchanged.  Particle.time is taken
+ * as 0 on entry (the reference leaves it uninitialised).
+ * results may be NULL. */
+int heroam_gpu_simulate_batch(heroam_ctx *ctx, unsigned long long he_number,
+                              heroam_particles *trajectories, int count,
+                              heroam_traj_result *results);
+
+/* Same on a flat batch: counts[count] particles per trajectory, records stored
+ * trajectory after trajectory in flat[]. */
+int heroam_gpu_simulate_flat(heroam_ctx *ctx, unsigned long long he_number,
+                             const uint32_t *counts, heroam_particle *flat, int count,
+                             heroam_traj_result *results);
+
+/* The same work split in three so that a benchmark can time the resident part:
+ * upload copies the batch to the device, run integrates it there (may be called
+ * once per upload), download copies the final states (and results) back. */
+int heroam_gpu_upload(heroam_ctx *ctx, unsigned long long he_number, const uint32_t *counts,
+                      const heroam_particle *flat, int count);
+int heroam_gpu_run(heroam_ctx *ctx);
+int heroam_gpu_download(heroam_ctx *ctx, heroam_particle *flat, heroam_traj_result *results);
+
+/* Philox replacement for initialize_particles (simulation.c:277-337): trajectory i of
+ * the call is trajectory (first_index + i) of the stream keyed by (conf->seed,
+ * he_number), so results do not depend on how a run is sharded.
+ *   _batch: fills out[i].no/.index and mallocs out[i].particle (release with
+ *           heroam_gpu_free_particles, or the reference's free_particles).
+ *   _flat : counts[count] and up to capacity records; *total receives the number of
+ *           records needed (call again with a larger buffer if it exceeds capacity). */
+int heroam_gpu_sample_batch(heroam_ctx *ctx, unsigned long long he_number,
+                            unsigned long long first_index, int count, heroam_particles *out);
+int heroam_gpu_sample_flat(heroam_ctx *ctx, unsigned long long he_number,
+                           unsigned long long first_index, int count, uint32_t *counts,
+                           heroam_particle *flat, long capacity, long *total);
+void heroam_gpu_free_particles(heroam_particles *p);
+
+/* Fused sample -> integrate -> histogram for large runs: nothing but counters and
+ * histograms comes back.  Works through [first_index, first_index + count) in
+ * device-resident batches. */
+int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number,
+                         unsigned long long first_index, unsigned long long count,
+                         heroam_stats *out);
+
+int heroam_gpu_last_run_info(const heroam_ctx *ctx, heroam_run_info *out);
+
+/* Register-resident FFMA microbenchmark on the context's device: the measured FP32
+ * peak used as the roofline denominator.  TFLOP/s. */
+int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEROAM_GPU_H_ */

@@ -249,12 +249,12 @@ orc_result orc_simulate_one(const heroam_config *conf, unsigned long long he_num
   float now = 0.0f; /* :467 */
   while (!done && now < c.max_time) { /* :469 */
     if (max_steps && res.steps >= max_steps) { res.status = ORC_DONE_STEPCAP; break; }
-    uint32_t moved = 0;
+    uint32_t moved = 0; /* particles that complete this step (their clock advances) */
     for (uint32_t i = 0; i < no; ++i)
-      if (!p[i].success) { kick_and_drift(&c, p + i, w_half + i); ++moved; }
+      if (!p[i].success) kick_and_drift(&c, p + i, w_half + i);
     forces_and_meetings(&c, no, p, table, ctr);
     for (uint32_t i = 0; i < no; ++i)
-      if (!p[i].success) kick_and_clock(&c, p + i, w_half[i]);
+      if (!p[i].success) { kick_and_clock(&c, p + i, w_half[i]); ++moved; }
     if (ctr) ctr->particle_steps += moved;
     res.steps++;
     float latest = p[0].time; /* :512-517 */
@@ -263,7 +263,7 @@ orc_result orc_simulate_one(const heroam_config *conf, unsigned long long he_num
     const int advanced = latest > now;
     now = latest;
     done = all_paired(no, p, &res.n_flagged);
-    if (!done) {
+    if (!done && now < c.max_time) { /* the reference's own exits take precedence */
       uint32_t active = 0;
       for (uint32_t i = 0; i < no; ++i) active += !p[i].success;
       /* DEFINED: nobody left to move and the == criterion is unmet -> the
@@ -472,3 +472,65 @@ int orc_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* known-answer entry points: expose the internal pieces so tests can pin    */
+/* them against the reference's vector.c / simulation.c one function at a    */
+/* time (tests/golden/vector_kats.npz, sampler_streams.npz)                  */
+/* ------------------------------------------------------------------------- */
+void orc_kat_cross(const float *a, const float *b, float *out) { st3(out, v3_cross(ld3(a), ld3(b))); }
+void orc_kat_add(const float *a, const float *b, float *out) { st3(out, v3_add(ld3(a), ld3(b))); }
+void orc_kat_scale(float s, const float *a, float *out) { st3(out, v3_scale(ld3(a), s)); }
+float orc_kat_norm(const float *a) { return v3_norm(ld3(a)); }
+float orc_kat_norm_sq(const float *a) { return v3_norm_sq(ld3(a)); }
+void orc_kat_tangent(const float *a, float *out) { st3(out, tangent_of(ld3(a))); }
+void orc_kat_qmul(const float *p, const float *q, float *out) { st4(out, qt_mul(ld4(p), ld4(q))); }
+void orc_kat_qinv(const float *q, float *out) { st4(out, qt_inverse(ld4(q))); }
+float orc_kat_qnorm(const float *q) { return qt_norm(ld4(q)); }
+void orc_kat_pole(const float *q, float *out) { st3(out, qt_pole_image(ld4(q))); }
+/* find_accelration + update_angvel + update_orientation on one particle */
+void orc_kat_accel(float mass, float radius, const float *pos, const float *force, float *acc) {
+  consts c;
+  memset(&c, 0, sizeof c);
+  c.acc_scale = (float)(1.0 / (double)mass / (double)radius / (double)radius);
+  heroam_particle p;
+  memset(&p, 0, sizeof p);
+  memcpy(p.position, pos, sizeof p.position);
+  memcpy(p.force, force, sizeof p.force);
+  st3(acc, ang_accel(&c, &p));
+}
+void orc_kat_orientation(float radius, float dt, float *quat, const float *w_half, float *pos) {
+  consts c;
+  memset(&c, 0, sizeof c);
+  c.radius = radius;
+  c.half_dt = (float)((double)dt / 2.0);
+  heroam_particle p;
+  memset(&p, 0, sizeof p);
+  memcpy(p.orientation, quat, sizeof p.orientation);
+  /* kick_and_drift with zero force leaves w_half == ang_velocity */
+  memcpy(p.ang_velocity, w_half, sizeof p.ang_velocity);
+  v3 wh;
+  kick_and_drift(&c, &p, &wh);
+  memcpy(quat, p.orientation, sizeof p.orientation);
+  memcpy(pos, p.position, sizeof p.position);
+}
+void orc_kat_poisson(unsigned int seed, double lambda, int n, int *out) {
+  draw_src s;
+  memset(&s, 0, sizeof s);
+  srand(seed);
+  const double limit = exp(-1.0 * lambda);
+  for (int i = 0; i < n; ++i) out[i] = poisson_knuth(&s, limit);
+}
+void orc_kat_speed(unsigned int seed, float sigma, int n, float *out) {
+  draw_src s;
+  memset(&s, 0, sizeof s);
+  srand(seed);
+  for (int i = 0; i < n; ++i) out[i] = thermal_speed(&s, sigma);
+}
+void orc_kat_quat(unsigned int seed, int n, float *out) {
+  draw_src s;
+  memset(&s, 0, sizeof s);
+  srand(seed);
+  for (int i = 0; i < n; ++i) st4(out + 4 * i, random_orientation(&s));
+}
+int orc_find_success(uint32_t no, const heroam_particle *p) { return all_paired(no, p, NULL); }

@@ -1,0 +1,323 @@
+// heroam_device.cuh -- device-side state layout and arithmetic of the trajectory
+// integrator (sm_100a).  Two arithmetic policies:
+//
+//   Exact : every float operation of the reference's step (simulation.c:478-509,
+//           :158-236, vector.c) in the reference's order through the never-contracted
+//           __f*_rn intrinsics; sqrt / reciprocal / divide correctly rounded (a double
+//           sqrt or divide of float operands narrowed to float equals the correctly
+//           rounded float result, so (float)sqrt((double)x) == __fsqrt_rn(x) and
+//           (float)(1.0/(double)x) == __frcp_rn(x)); the one genuinely double
+//           expression, Force_list[i]/sqrt(d) (simulation.c:220), in double.
+//           Terms the reference multiplies by a literal 0 or 1 are dropped: they change
+//           at most the sign of an exact zero, never a value.
+//   Fast  : same state and integrator; FMA contraction, closed-form pole image,
+//           MUFU rsqrt.  The GPU counterpart of the reference's -ffast-math build.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/heroam_gpu.h"
+
+namespace heroam {
+
+// Trajectory status while it is being worked on (device side only).
+enum : uint32_t {
+  ST_LIVE = 0,     // clean state at a step boundary
+  ST_MIDSTEP = 1,  // a pair came within icd_dist during the step: drift done, greedy
+                   // meeting sweep + force + second kick still to do (resolve kernel)
+  ST_DONE = 16     // ST_DONE + HEROAM_DONE_* once finished
+};
+
+struct TrajMeta {      // 32 bytes per trajectory
+  uint32_t first;      // first record of this trajectory in the flat particle array
+  uint32_t no;         // particles in the trajectory
+  uint32_t steps;      // completed iterations of the step loop
+  float time;          // the loop's `time` variable (simulation.c:467, :512-517)
+  uint32_t n_flagged;  // particles with success == 1
+  uint32_t n_active;   // particles still moving
+  uint32_t status;     // ST_*
+  uint32_t step_stop;  // the integrate kernel pauses when steps reaches this
+};
+
+// Loop-invariant scalars, rounded on the host exactly where the reference rounds them.
+struct Consts {
+  float dt;          // simulation.c:443
+  float half_dt;     // (float)(dt / 2.0)                       :486, :502, :406
+  float radius;      // (float)(2.22 * pow((float)N, 1.0/3.0))  :448
+  float acc_scale;   // (float)(1.0 / mass / radius / radius)   :351
+  float inv_grid;    // (float)(1.0 / force_grid)               :162
+  float grid_start;  // :163
+  float icd2;        // icd_dist * icd_dist (float product)     :164
+  float max_time;    // :469
+  int grid_len;      // :219 (clamped to INT_MAX on the host)
+  uint32_t max_steps;   // steps until the float clock reaches max_time (host-iterated)
+  // fast-mode folded constants
+  float kick;        // acc_scale * half_dt
+  float radius2;     // 2 * radius
+};
+
+struct Counters {     // roofline work counters
+  unsigned long long particle_steps;
+  unsigned long long pair_steps;
+  unsigned long long inrange_steps;
+  unsigned long long unsupported;   // trajectories refused for having too many moving particles
+};
+
+struct DevView {       // everything a kernel needs, passed by value
+  Consts c;
+  const float *__restrict__ table;
+  heroam_particle *particles;
+  TrajMeta *meta;
+  uint32_t *act;       // act[first + s] = index (within the trajectory) of its s-th active particle
+  Counters *counters;
+  uint32_t n_traj;
+};
+
+// ---------------------------------------------------------------------------------
+// arithmetic policies
+// ---------------------------------------------------------------------------------
+struct Exact {
+  static constexpr bool exact = true;
+  __device__ __forceinline__ static float mul(float a, float b) { return __fmul_rn(a, b); }
+  __device__ __forceinline__ static float add(float a, float b) { return __fadd_rn(a, b); }
+  __device__ __forceinline__ static float sub(float a, float b) { return __fsub_rn(a, b); }
+  // a*b - c*d and a*b + c*d with three roundings, as written in the reference
+  __device__ __forceinline__ static float mm_sub(float a, float b, float c, float d) {
+    return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+  }
+  __device__ __forceinline__ static float mm_add(float a, float b, float c, float d) {
+    return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+  }
+  // acc + a*b / acc - a*b (two roundings)
+  __device__ __forceinline__ static float acc_add(float acc, float a, float b) {
+    return __fadd_rn(acc, __fmul_rn(a, b));
+  }
+  __device__ __forceinline__ static float acc_sub(float acc, float a, float b) {
+    return __fsub_rn(acc, __fmul_rn(a, b));
+  }
+  __device__ __forceinline__ static float dot3(float x, float y, float z) {  // x*x + y*y + z*z
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  }
+  __device__ __forceinline__ static float dot4(float a, float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(x, x)), __fmul_rn(y, y)),
+                     __fmul_rn(z, z));
+  }
+};
+
+struct Fast {
+  static constexpr bool exact = false;
+  __device__ __forceinline__ static float mul(float a, float b) { return a * b; }
+  __device__ __forceinline__ static float add(float a, float b) { return a + b; }
+  __device__ __forceinline__ static float sub(float a, float b) { return a - b; }
+  __device__ __forceinline__ static float mm_sub(float a, float b, float c, float d) {
+    return fmaf(a, b, -(c * d));
+  }
+  __device__ __forceinline__ static float mm_add(float a, float b, float c, float d) {
+    return fmaf(a, b, c * d);
+  }
+  __device__ __forceinline__ static float acc_add(float acc, float a, float b) { return fmaf(a, b, acc); }
+  __device__ __forceinline__ static float acc_sub(float acc, float a, float b) { return fmaf(-a, b, acc); }
+  __device__ __forceinline__ static float dot3(float x, float y, float z) {
+    return fmaf(z, z, fmaf(y, y, x * x));
+  }
+  __device__ __forceinline__ static float dot4(float a, float x, float y, float z) {
+    return fmaf(z, z, fmaf(y, y, fmaf(x, x, a * a)));
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// per-particle pieces of a step
+// ---------------------------------------------------------------------------------
+// (dt/2) * angular acceleration: find_accelration (simulation.c:343-352) followed by the
+// scalar_multiply of update_angvel (:354-361).  The same value serves the second kick of
+// one step and the first kick of the next (same position, same force).
+template <class P>
+__device__ __forceinline__ void half_kick(const Consts &c, const float r[3], const float f[3],
+                                          float hk[3]) {
+  const float tx = P::mm_sub(r[1], f[2], r[2], f[1]);
+  const float ty = P::mm_sub(r[2], f[0], r[0], f[2]);
+  const float tz = P::mm_sub(r[0], f[1], r[1], f[0]);
+  if (P::exact) {
+    hk[0] = P::mul(P::mul(tx, c.acc_scale), c.half_dt);
+    hk[1] = P::mul(P::mul(ty, c.acc_scale), c.half_dt);
+    hk[2] = P::mul(P::mul(tz, c.acc_scale), c.half_dt);
+  } else {
+    hk[0] = tx * c.kick;
+    hk[1] = ty * c.kick;
+    hk[2] = tz * c.kick;
+  }
+}
+
+// update_orientation (simulation.c:394-413): q += (dt/2) (0,w) q ; q /= |q| ;
+// r = R * q (0,0,1) q^-1  (vector.c:94-110, :191-205, :182-188).
+template <class P>
+__device__ __forceinline__ void drift(const Consts &c, const float w[3], float q[4], float r[3]) {
+  const float qa = q[0], qx = q[1], qy = q[2], qz = q[3];
+  const float ox = w[0], oy = w[1], oz = w[2];
+  if (P::exact) {
+    // (0,w) (x) q, vector.c:166-171 with the zero scalar part dropped
+    const float ta = P::sub(P::sub(-P::mul(ox, qx), P::mul(oy, qy)), P::mul(oz, qz));
+    const float tx = P::sub(P::add(P::mul(ox, qa), P::mul(oy, qz)), P::mul(oz, qy));
+    const float ty = P::add(P::sub(P::mul(oy, qa), P::mul(ox, qz)), P::mul(oz, qx));
+    const float tz = P::add(P::sub(P::mul(ox, qy), P::mul(oy, qx)), P::mul(oz, qa));
+    float na = P::add(qa, P::mul(ta, c.half_dt));
+    float nx = P::add(qx, P::mul(tx, c.half_dt));
+    float ny = P::add(qy, P::mul(ty, c.half_dt));
+    float nz = P::add(qz, P::mul(tz, c.half_dt));
+    const float inv = __frcp_rn(__fsqrt_rn(P::dot4(na, nx, ny, nz)));
+    na = P::mul(na, inv); nx = P::mul(nx, inv); ny = P::mul(ny, inv); nz = P::mul(nz, inv);
+    q[0] = na; q[1] = nx; q[2] = ny; q[3] = nz;
+    // q^-1 = conj(q)/|q|^2 ; t = q (x) (0,0,0,1) = (-qz, qy, -qx, qa) ; res = t (x) q^-1
+    const float n2 = P::dot4(na, nx, ny, nz);
+    const float ia = __fdiv_rn(na, n2);
+    const float ix = -__fdiv_rn(nx, n2);
+    const float iy = -__fdiv_rn(ny, n2);
+    const float iz = -__fdiv_rn(nz, n2);
+    const float ua = -nz, ux = ny, uy = -nx, uz = na;
+    const float rx = P::sub(P::add(P::add(P::mul(ua, ix), P::mul(ux, ia)), P::mul(uy, iz)), P::mul(uz, iy));
+    const float ry = P::add(P::add(P::sub(P::mul(ua, iy), P::mul(ux, iz)), P::mul(uy, ia)), P::mul(uz, ix));
+    const float rz = P::add(P::sub(P::add(P::mul(ua, iz), P::mul(ux, iy)), P::mul(uy, ix)), P::mul(uz, ia));
+    r[0] = P::mul(rx, c.radius);
+    r[1] = P::mul(ry, c.radius);
+    r[2] = P::mul(rz, c.radius);
+  } else {
+    const float ta = -fmaf(oz, qz, fmaf(oy, qy, ox * qx));
+    const float tx = fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
+    const float ty = fmaf(oz, qx, fmaf(-ox, qz, oy * qa));
+    const float tz = fmaf(oz, qa, fmaf(-oy, qx, ox * qy));
+    float na = fmaf(ta, c.half_dt, qa);
+    float nx = fmaf(tx, c.half_dt, qx);
+    float ny = fmaf(ty, c.half_dt, qy);
+    float nz = fmaf(tz, c.half_dt, qz);
+    const float inv = rsqrtf(P::dot4(na, nx, ny, nz));
+    na *= inv; nx *= inv; ny *= inv; nz *= inv;
+    q[0] = na; q[1] = nx; q[2] = ny; q[3] = nz;
+    // unit q: q (0,0,1) q^-1 = (2(xz + ay), 2(yz - ax), a^2 - x^2 - y^2 + z^2)
+    r[0] = c.radius2 * fmaf(nx, nz, na * ny);
+    r[1] = c.radius2 * fmaf(ny, nz, -(na * nx));
+    r[2] = c.radius * (fmaf(na, na, nz * nz) - fmaf(nx, nx, ny * ny));
+  }
+}
+
+// One pair (simulation.c:192-197 and :216-229).  Returns d; adds the table force to
+// fj / subtracts it from fk when the squared distance falls inside the table.
+// Out-of-table (either side) means "no force" (SURVEY.md Q5).
+template <class P>
+__device__ __forceinline__ float pair_force(const Consts &c, const float *__restrict__ table,
+                                            const float rj[3], const float rk[3], float fj[3],
+                                            float fk[3], uint32_t &inrange) {
+  const float dx = P::sub(rj[0], rk[0]);
+  const float dy = P::sub(rj[1], rk[1]);
+  const float dz = P::sub(rj[2], rk[2]);
+  const float d = P::dot3(dx, dy, dz);
+  // bin = (int)((d - start) * inv_grid) in float, as the reference (Q6)
+  const float pos = __fmul_rn(__fsub_rn(d, c.grid_start), c.inv_grid);
+  const int bin = __float2int_rz(pos);
+  if (pos > -1.0f && bin < c.grid_len) {
+    ++inrange;
+    const float tv = __ldg(table + bin);
+    float scale;
+    if (P::exact) {
+      scale = __double2float_rn(__ddiv_rn((double)tv, __dsqrt_rn((double)d)));
+      const float fx = P::mul(scale, dx), fy = P::mul(scale, dy), fz = P::mul(scale, dz);
+      fj[0] = P::add(fj[0], fx); fj[1] = P::add(fj[1], fy); fj[2] = P::add(fj[2], fz);
+      fk[0] = P::sub(fk[0], fx); fk[1] = P::sub(fk[1], fy); fk[2] = P::sub(fk[2], fz);
+    } else {
+      scale = tv * rsqrtf(d);
+      fj[0] = fmaf(scale, dx, fj[0]); fj[1] = fmaf(scale, dy, fj[1]); fj[2] = fmaf(scale, dz, fj[2]);
+      fk[0] = fmaf(-scale, dx, fk[0]); fk[1] = fmaf(-scale, dy, fk[1]); fk[2] = fmaf(-scale, dz, fk[2]);
+    }
+  }
+  return d;
+}
+
+// The same pair split in three branch-free stages so that a kernel can issue the table
+// gathers of many pairs back to back and only then consume them (memory-level parallelism
+// instead of one exposed L1/L2 latency per pair):
+//   pair_geom   : separation, squared distance, table bin (clamped to 0 when outside)
+//   pair_gather : the table value, 0 outside the table
+//   pair_scale  : Force_list[bin] / sqrt(d)   (simulation.c:220)
+// A pair outside the table contributes scale == 0, i.e. adds +-0 to both forces, which
+// leaves every value as the reference's "skip" does.
+struct PairGeom {
+  float dx, dy, dz, d;
+  int bin;      // valid table index (0 when the pair is outside the table)
+  bool inside;
+};
+
+template <class P>
+__device__ __forceinline__ PairGeom pair_geom(const Consts &c, const float rj[3], const float rk[3]) {
+  PairGeom g;
+  g.dx = P::sub(rj[0], rk[0]);
+  g.dy = P::sub(rj[1], rk[1]);
+  g.dz = P::sub(rj[2], rk[2]);
+  g.d = P::dot3(g.dx, g.dy, g.dz);
+  const float pos = __fmul_rn(__fsub_rn(g.d, c.grid_start), c.inv_grid);  // float, as the reference (Q6)
+  const int bin = __float2int_rz(pos);
+  g.inside = pos > -1.0f && bin < c.grid_len;
+  g.bin = g.inside ? bin : 0;
+  return g;
+}
+
+__device__ __forceinline__ float pair_gather(const float *__restrict__ table, const PairGeom &g) {
+  const float tv = __ldg(table + g.bin);
+  return g.inside ? tv : 0.0f;
+}
+
+template <class P>
+__device__ __forceinline__ float pair_scale(float tv, float d) {
+  if (P::exact) return __double2float_rn(__ddiv_rn((double)tv, __dsqrt_rn((double)d)));
+  return tv * rsqrtf(d);
+}
+
+// F_j += scale * (r_j - r_k) ; F_k -= scale * (r_j - r_k)   (simulation.c:221-229)
+template <class P>
+__device__ __forceinline__ void pair_apply(float scale, const PairGeom &g, float fj[3], float fk[3]) {
+  if (P::exact) {
+    const float fx = P::mul(scale, g.dx), fy = P::mul(scale, g.dy), fz = P::mul(scale, g.dz);
+    fj[0] = P::add(fj[0], fx); fj[1] = P::add(fj[1], fy); fj[2] = P::add(fj[2], fz);
+    fk[0] = P::sub(fk[0], fx); fk[1] = P::sub(fk[1], fy); fk[2] = P::sub(fk[2], fz);
+  } else {
+    fj[0] = fmaf(scale, g.dx, fj[0]); fj[1] = fmaf(scale, g.dy, fj[1]); fj[2] = fmaf(scale, g.dz, fj[2]);
+    fk[0] = fmaf(-scale, g.dx, fk[0]); fk[1] = fmaf(-scale, g.dy, fk[1]); fk[2] = fmaf(-scale, g.dz, fk[2]);
+  }
+}
+// one-sided form for kernels in which every particle accumulates its own force
+template <class P>
+__device__ __forceinline__ void pair_apply_own(float scale, const PairGeom &g, float fj[3]) {
+  if (P::exact) {
+    fj[0] = P::add(fj[0], P::mul(scale, g.dx));
+    fj[1] = P::add(fj[1], P::mul(scale, g.dy));
+    fj[2] = P::add(fj[2], P::mul(scale, g.dz));
+  } else {
+    fj[0] = fmaf(scale, g.dx, fj[0]); fj[1] = fmaf(scale, g.dy, fj[1]); fj[2] = fmaf(scale, g.dz, fj[2]);
+  }
+}
+
+// squared distance only (meeting sweep, simulation.c:192-196)
+template <class P>
+__device__ __forceinline__ float pair_dist_sq(const float rj[3], const float rk[3]) {
+  return P::dot3(P::sub(rj[0], rk[0]), P::sub(rj[1], rk[1]), P::sub(rj[2], rk[2]));
+}
+
+// stored velocity r x w (simulation.c:504) and its square (:506)
+template <class P>
+__device__ __forceinline__ void stored_velocity(const float r[3], const float w[3], float v[3], float &v2) {
+  v[0] = P::mm_sub(r[1], w[2], r[2], w[1]);
+  v[1] = P::mm_sub(r[2], w[0], r[0], w[2]);
+  v[2] = P::mm_sub(r[0], w[1], r[1], w[0]);
+  v2 = P::dot3(v[0], v[1], v[2]);
+}
+
+// |f| as norm() of vector.c:24-26
+__device__ __forceinline__ float vec_norm(const float f[3]) {
+  return __fsqrt_rn(Exact::dot3(f[0], f[1], f[2]));
+}
+
+// find_success (simulation.c:33-46): equality, not >= (Q4)
+__device__ __forceinline__ bool all_paired(uint32_t no, uint32_t flagged) {
+  return (no & 1u) ? (flagged == no - 1u) : (flagged == no);
+}
+
+}  // namespace heroam

@@ -1,0 +1,491 @@
+// heroam_gpu.cu -- C ABI (include/heroam_gpu.h) over the CUDA kernels.
+// Host side of the engine: context, buffers, the pass loop, copies, timing.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "heroam_kernels.cuh"
+
+using namespace heroam;
+
+// ---------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(HEROAM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                  \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------
+struct heroam_ctx {
+  int device = 0;
+  heroam_config conf;
+  heroam_options opt;
+  cudaStream_t main = nullptr;
+  cudaStream_t bin_stream[N_BINS] = {};
+  cudaEvent_t bin_done[N_BINS] = {};
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_i0 = nullptr, ev_i1 = nullptr, ev_c0 = nullptr,
+              ev_c1 = nullptr;
+  float *d_table = nullptr;
+  long table_len = 0;
+  // batch buffers (grown on demand)
+  heroam_particle *d_particles = nullptr;
+  size_t cap_particles = 0;
+  TrajMeta *d_meta = nullptr;
+  uint32_t *d_act = nullptr, *d_first = nullptr, *d_counts = nullptr, *d_bin_list = nullptr;
+  heroam_traj_result *d_results = nullptr;
+  size_t cap_traj = 0;
+  uint32_t *d_bin_count = nullptr;
+  Counters *d_counters = nullptr;
+  uint32_t *h_bin_count = nullptr;  // pinned
+  Counters *h_counters = nullptr;   // pinned
+  // current batch
+  unsigned long long he_number = 0;
+  uint32_t n_traj = 0;
+  size_t n_particles = 0;
+  bool uploaded = false;
+  heroam_run_info info;
+  int sm_count = 0;
+};
+
+extern "C" int heroam_gpu_abi_version(void) { return HEROAM_ABI_VERSION; }
+
+extern "C" int heroam_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" const char *heroam_gpu_last_error(void) { return g_err; }
+
+// Steps until the reference's float clock reaches max_time, iterated exactly as the
+// reference accumulates it (particle->time += dt, simulation.c:507).  Returns false when
+// the clock stops advancing first: the reference would then loop forever (Q10).
+static bool clock_steps(float dt, float max_time, uint32_t *steps_out) {
+  float t = 0.0f;
+  uint64_t k = 0;
+  while (t < max_time) {
+    const float next = t + dt;
+    if (!(next > t)) return false;
+    t = next;
+    if (++k >= 0xfffffff0ull) return false;
+  }
+  *steps_out = (uint32_t)k;
+  return true;
+}
+
+static int make_consts(const heroam_config &conf, unsigned long long he_number, Consts *out) {
+  Consts c;
+  c.dt = conf.dt;
+  c.half_dt = (float)((double)conf.dt / 2.0);
+  c.radius = (float)(2.22 * pow((double)(float)he_number, 1.0 / 3.0));
+  c.acc_scale = (float)(1.0 / (double)conf.mass / (double)c.radius / (double)c.radius);
+  c.inv_grid = (float)(1.0 / (double)conf.force_grid);
+  c.grid_start = conf.force_grid_start;
+  c.icd2 = conf.icd_dist * conf.icd_dist;
+  c.max_time = conf.max_time;
+  c.grid_len = conf.force_grid_length > 0x7fffffffL ? 0x7fffffff : (int)conf.force_grid_length;
+  if (!(conf.dt > 0.0f)) return fail(HEROAM_E_ARG, "dt must be positive (got %g)", (double)conf.dt);
+  if (!clock_steps(conf.dt, conf.max_time, &c.max_steps))
+    return fail(HEROAM_E_CLOCK,
+                "dt=%g cannot advance a float clock up to max_time=%g: the reference's loop would never end",
+                (double)conf.dt, (double)conf.max_time);
+  c.kick = c.acc_scale * c.half_dt;
+  c.radius2 = 2.0f * c.radius;
+  *out = c;
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_list, int device,
+                                 const heroam_options *opt, heroam_ctx **out) {
+  if (!conf || !force_list || !out) return fail(HEROAM_E_ARG, "heroam_gpu_create: null argument");
+  if (conf->force_grid_length <= 0) return fail(HEROAM_E_ARG, "force_grid_length must be positive");
+  if (!(conf->force_grid > 0.0f)) return fail(HEROAM_E_ARG, "force_grid must be positive");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) return fail(HEROAM_E_CUDA, "no CUDA device: this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(HEROAM_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(HEROAM_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  heroam_ctx *ctx = new heroam_ctx();
+  ctx->device = device;
+  ctx->conf = *conf;
+  memset(&ctx->opt, 0, sizeof ctx->opt);
+  if (opt) ctx->opt = *opt;
+  if (ctx->opt.mode != HEROAM_MODE_EXACT && ctx->opt.mode != HEROAM_MODE_FAST) {
+    delete ctx;
+    return fail(HEROAM_E_ARG, "unknown mode %d", opt->mode);
+  }
+  if (ctx->opt.segment_steps == 0) ctx->opt.segment_steps = 8192;
+  ctx->sm_count = prop.multiProcessorCount;
+  memset(&ctx->info, 0, sizeof ctx->info);
+  ctx->table_len = conf->force_grid_length;
+  CU(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
+  for (int b = 0; b < N_BINS; ++b) {
+    CU(cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->bin_done[b], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreate(&ctx->ev_start));
+  CU(cudaEventCreate(&ctx->ev_stop));
+  CU(cudaEventCreate(&ctx->ev_i0));
+  CU(cudaEventCreate(&ctx->ev_i1));
+  CU(cudaEventCreate(&ctx->ev_c0));
+  CU(cudaEventCreate(&ctx->ev_c1));
+  CU(cudaMalloc(&ctx->d_table, (size_t)ctx->table_len * sizeof(float)));
+  CU(cudaMemcpy(ctx->d_table, force_list, (size_t)ctx->table_len * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&ctx->d_bin_count, N_BINS * sizeof(uint32_t)));
+  CU(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
+  CU(cudaMallocHost(&ctx->h_bin_count, N_BINS * sizeof(uint32_t)));
+  CU(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
+  *out = ctx;
+  return HEROAM_OK;
+}
+
+extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  cudaFree(ctx->d_table);
+  cudaFree(ctx->d_particles);
+  cudaFree(ctx->d_meta);
+  cudaFree(ctx->d_act);
+  cudaFree(ctx->d_first);
+  cudaFree(ctx->d_counts);
+  cudaFree(ctx->d_bin_list);
+  cudaFree(ctx->d_results);
+  cudaFree(ctx->d_bin_count);
+  cudaFree(ctx->d_counters);
+  cudaFreeHost(ctx->h_bin_count);
+  cudaFreeHost(ctx->h_counters);
+  for (int b = 0; b < N_BINS; ++b) {
+    if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
+    if (ctx->bin_done[b]) cudaEventDestroy(ctx->bin_done[b]);
+  }
+  cudaEvent_t evs[] = {ctx->ev_start, ctx->ev_stop, ctx->ev_i0, ctx->ev_i1, ctx->ev_c0, ctx->ev_c1};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  if (ctx->main) cudaStreamDestroy(ctx->main);
+  delete ctx;
+}
+
+extern "C" int heroam_gpu_set_mode(heroam_ctx *ctx, int mode) {
+  if (!ctx) return fail(HEROAM_E_ARG, "null context");
+  if (mode != HEROAM_MODE_EXACT && mode != HEROAM_MODE_FAST) return fail(HEROAM_E_ARG, "unknown mode %d", mode);
+  ctx->opt.mode = mode;
+  return HEROAM_OK;
+}
+
+// grow the per-batch device buffers
+static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
+  if (n_particles > ctx->cap_particles) {
+    cudaFree(ctx->d_particles);
+    cudaFree(ctx->d_act);
+    ctx->d_particles = nullptr;
+    ctx->d_act = nullptr;
+    ctx->cap_particles = 0;
+    CU(cudaMalloc(&ctx->d_particles, n_particles * sizeof(heroam_particle)));
+    CU(cudaMalloc(&ctx->d_act, n_particles * sizeof(uint32_t)));
+    ctx->cap_particles = n_particles;
+  }
+  if (n_traj > ctx->cap_traj) {
+    cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_first);
+    cudaFree(ctx->d_counts);
+    cudaFree(ctx->d_bin_list);
+    cudaFree(ctx->d_results);
+    ctx->d_meta = nullptr;
+    ctx->d_first = ctx->d_counts = ctx->d_bin_list = nullptr;
+    ctx->d_results = nullptr;
+    ctx->cap_traj = 0;
+    CU(cudaMalloc(&ctx->d_meta, n_traj * sizeof(TrajMeta)));
+    CU(cudaMalloc(&ctx->d_first, n_traj * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_counts, n_traj * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_bin_list, (size_t)N_BINS * n_traj * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_results, n_traj * sizeof(heroam_traj_result)));
+    ctx->cap_traj = n_traj;
+  }
+  return HEROAM_OK;
+}
+
+static DevView make_view(heroam_ctx *ctx, const Consts &c) {
+  DevView v;
+  v.c = c;
+  v.table = ctx->d_table;
+  v.particles = ctx->d_particles;
+  v.meta = ctx->d_meta;
+  v.act = ctx->d_act;
+  v.counters = ctx->d_counters;
+  v.n_traj = ctx->n_traj;
+  return v;
+}
+
+extern "C" int heroam_gpu_upload(heroam_ctx *ctx, unsigned long long he_number, const uint32_t *counts,
+                                 const heroam_particle *flat, int count) {
+  if (!ctx || !counts || (!flat && count > 0) || count < 0) return fail(HEROAM_E_ARG, "heroam_gpu_upload: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<uint32_t> first((size_t)count);
+  size_t total = 0;
+  for (int i = 0; i < count; ++i) {
+    if (counts[i] == 0) return fail(HEROAM_E_ARG, "trajectory %d has no particles", i);
+    first[i] = (uint32_t)total;
+    total += counts[i];
+    if (total > 0xfffffff0ull) return fail(HEROAM_E_ARG, "batch too large: more than 2^32 particle records");
+  }
+  int rc = reserve(ctx, (size_t)count > 0 ? (size_t)count : 1, total > 0 ? total : 1);
+  if (rc) return rc;
+  ctx->he_number = he_number;
+  ctx->n_traj = (uint32_t)count;
+  ctx->n_particles = total;
+  memset(&ctx->info, 0, sizeof ctx->info);
+  CU(cudaEventRecord(ctx->ev_c0, ctx->main));
+  if (count > 0) {
+    CU(cudaMemcpyAsync(ctx->d_particles, flat, total * sizeof(heroam_particle), cudaMemcpyHostToDevice, ctx->main));
+    CU(cudaMemcpyAsync(ctx->d_counts, counts, (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->main));
+    CU(cudaMemcpyAsync(ctx->d_first, first.data(), (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->main));
+  }
+  CU(cudaEventRecord(ctx->ev_c1, ctx->main));
+  CU(cudaStreamSynchronize(ctx->main));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, ctx->ev_c0, ctx->ev_c1));
+  ctx->info.h2d_ms = ms;
+  ctx->info.h2d_bytes = total * sizeof(heroam_particle) + 2ull * count * sizeof(uint32_t);
+  ctx->uploaded = true;
+  return HEROAM_OK;
+}
+
+template <class P>
+static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) {
+  const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
+  cudaStream_t s = ctx->bin_stream[bin];
+  const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
+  switch (bin) {
+    case 1: k_integrate_thread<1, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    case 2: k_integrate_thread<2, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    case 3: k_integrate_thread<3, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    case 4: k_integrate_thread<4, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    case 5: k_integrate_thread<5, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    case 6: k_integrate_thread<6, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    case 7: k_integrate_thread<7, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    case 8: k_integrate_thread<8, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
+    default: {
+      const unsigned wgrid = (cnt + WARP_KERNEL_WARPS - 1) / WARP_KERNEL_WARPS;
+      if (ctx->opt.wide_kernel == 1) k_integrate_records<P><<<(cnt + 63) / 64, 64, 0, s>>>(v, list, cnt);
+      else if (bin == BIN_WARP1) k_integrate_warp<1, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+      else if (bin == BIN_WARP2) k_integrate_warp<2, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+      else k_integrate_warp<4, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+      break;
+    }
+  }
+  CU(cudaGetLastError());
+  return HEROAM_OK;
+}
+
+template <class P>
+static int run_passes(heroam_ctx *ctx, const Consts &c) {
+  DevView v = make_view(ctx, c);
+  const uint32_t n = ctx->n_traj;
+  const unsigned tgrid = (n + 127) / 128;
+  const uint32_t cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu
+                                                                                    : (uint32_t)ctx->opt.max_steps;
+  double integrate_ms = 0.0;
+  bool pending_timing = false;
+  CU(cudaEventRecord(ctx->ev_start, ctx->main));
+  CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
+  k_prepare<<<tgrid, 128, 0, ctx->main>>>(v, ctx->d_first, ctx->d_counts);
+  CU(cudaGetLastError());
+  ctx->info.kernel_launches++;
+  for (;;) {
+    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
+    k_resolve_and_bin<P><<<tgrid, 128, 0, ctx->main>>>(v, ctx->opt.segment_steps, cap, ctx->d_bin_count, ctx->d_bin_list);
+    CU(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaStreamSynchronize(ctx->main));
+    if (pending_timing) {
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, ctx->ev_i0, ctx->ev_i1));
+      integrate_ms += ms;
+      pending_timing = false;
+    }
+    uint64_t live = 0;
+    for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
+    if (live == 0) break;
+    ctx->info.passes++;
+    CU(cudaEventRecord(ctx->ev_i0, ctx->main));
+    for (int b = 1; b < N_BINS; ++b) {
+      const uint32_t cnt = ctx->h_bin_count[b];
+      if (!cnt) continue;
+      // the bin streams start after ev_i0, i.e. after this pass's resolve kernel
+      CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
+      int rc = launch_bin<P>(ctx, v, b, cnt);
+      if (rc) return rc;
+      ctx->info.kernel_launches++;
+      CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
+      CU(cudaStreamWaitEvent(ctx->main, ctx->bin_done[b], 0));
+    }
+    CU(cudaEventRecord(ctx->ev_i1, ctx->main));
+    pending_timing = true;
+  }
+  k_results<<<tgrid, 128, 0, ctx->main>>>(v, ctx->d_results);
+  CU(cudaGetLastError());
+  ctx->info.kernel_launches++;
+  CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->main));
+  CU(cudaEventRecord(ctx->ev_stop, ctx->main));
+  CU(cudaStreamSynchronize(ctx->main));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+  ctx->info.device_ms = ms;
+  ctx->info.integrate_ms = integrate_ms;
+  ctx->info.particle_steps = ctx->h_counters->particle_steps;
+  ctx->info.pair_steps = ctx->h_counters->pair_steps;
+  ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
+  ctx->info.trajectories = n;
+  ctx->info.particles = ctx->n_particles;
+  if (ctx->h_counters->unsupported)
+    return fail(HEROAM_E_UNSUPPORTED, "%llu trajectories have more than %d moving particles", ctx->h_counters->unsupported,
+                MAX_ACTIVE);
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_run(heroam_ctx *ctx) {
+  if (!ctx) return fail(HEROAM_E_ARG, "null context");
+  if (!ctx->uploaded) return fail(HEROAM_E_ARG, "heroam_gpu_run: nothing uploaded");
+  CU(cudaSetDevice(ctx->device));
+  Consts c;
+  int rc = make_consts(ctx->conf, ctx->he_number, &c);
+  if (rc) return rc;
+  ctx->uploaded = false;  // the resident batch is consumed
+  if (ctx->n_traj == 0) return HEROAM_OK;
+  rc = ctx->opt.mode == HEROAM_MODE_EXACT ? run_passes<Exact>(ctx, c) : run_passes<Fast>(ctx, c);
+  return rc;
+}
+
+extern "C" int heroam_gpu_download(heroam_ctx *ctx, heroam_particle *flat, heroam_traj_result *results) {
+  if (!ctx) return fail(HEROAM_E_ARG, "null context");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev_c0, ctx->main));
+  size_t bytes = 0;
+  if (flat && ctx->n_particles) {
+    CU(cudaMemcpyAsync(flat, ctx->d_particles, ctx->n_particles * sizeof(heroam_particle), cudaMemcpyDeviceToHost, ctx->main));
+    bytes += ctx->n_particles * sizeof(heroam_particle);
+  }
+  if (results && ctx->n_traj) {
+    CU(cudaMemcpyAsync(results, ctx->d_results, (size_t)ctx->n_traj * sizeof(heroam_traj_result), cudaMemcpyDeviceToHost, ctx->main));
+    bytes += (size_t)ctx->n_traj * sizeof(heroam_traj_result);
+  }
+  CU(cudaEventRecord(ctx->ev_c1, ctx->main));
+  CU(cudaStreamSynchronize(ctx->main));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, ctx->ev_c0, ctx->ev_c1));
+  ctx->info.d2h_ms = ms;
+  ctx->info.d2h_bytes = bytes;
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_simulate_flat(heroam_ctx *ctx, unsigned long long he_number, const uint32_t *counts,
+                                        heroam_particle *flat, int count, heroam_traj_result *results) {
+  int rc = heroam_gpu_upload(ctx, he_number, counts, flat, count);
+  if (rc) return rc;
+  rc = heroam_gpu_run(ctx);
+  if (rc) return rc;
+  return heroam_gpu_download(ctx, flat, results);
+}
+
+extern "C" int heroam_gpu_simulate_batch(heroam_ctx *ctx, unsigned long long he_number,
+                                         heroam_particles *trajectories, int count, heroam_traj_result *results) {
+  if (!ctx || (!trajectories && count > 0) || count < 0) return fail(HEROAM_E_ARG, "heroam_gpu_simulate_batch: bad argument");
+  std::vector<uint32_t> counts((size_t)count);
+  size_t total = 0;
+  for (int i = 0; i < count; ++i) {
+    if (!trajectories[i].particle || trajectories[i].no == 0)
+      return fail(HEROAM_E_ARG, "trajectory %d is empty", i);
+    counts[i] = trajectories[i].no;
+    total += counts[i];
+  }
+  std::vector<heroam_particle> flat(total);
+  size_t at = 0;
+  for (int i = 0; i < count; ++i) {
+    memcpy(flat.data() + at, trajectories[i].particle, (size_t)counts[i] * sizeof(heroam_particle));
+    at += counts[i];
+  }
+  int rc = heroam_gpu_simulate_flat(ctx, he_number, counts.data(), flat.data(), count, results);
+  if (rc) return rc;
+  at = 0;
+  for (int i = 0; i < count; ++i) {
+    memcpy(trajectories[i].particle, flat.data() + at, (size_t)counts[i] * sizeof(heroam_particle));
+    at += counts[i];
+  }
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_last_run_info(const heroam_ctx *ctx, heroam_run_info *out) {
+  if (!ctx || !out) return fail(HEROAM_E_ARG, "null argument");
+  *out = ctx->info;
+  return HEROAM_OK;
+}
+
+extern "C" void heroam_gpu_free_particles(heroam_particles *p) {
+  if (p) {
+    free(p->particle);
+    p->particle = nullptr;
+  }
+}
+
+extern "C" int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_clock_mhz) {
+  if (!ctx || !tflops) return fail(HEROAM_E_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  float *d_out = nullptr;
+  CU(cudaMalloc(&d_out, sizeof(float)));
+  const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(ctx->ev_c0, ctx->main));
+    k_fma_peak<<<blocks, threads, 0, ctx->main>>>(d_out, iters, 0.999f, 0.001f);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_c1, ctx->main));
+    CU(cudaStreamSynchronize(ctx->main));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev_c0, ctx->ev_c1));
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaFree(d_out);
+  *tflops = best;
+  if (sm_clock_mhz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    *sm_clock_mhz = khz / 1000.0;
+  }
+  return HEROAM_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// sampler and fused statistics: see heroam_sampler.cuh
+// ---------------------------------------------------------------------------------
+#include "heroam_sampler.cuh"

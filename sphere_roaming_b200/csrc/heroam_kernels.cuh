@@ -1,0 +1,648 @@
+// heroam_kernels.cuh -- CUDA kernels of the trajectory engine (sm_100a).
+//
+// Work decomposition:
+//   * a trajectory whose `a` particles are still moving behaves exactly like an
+//     a-particle system: frozen particles neither exert nor feel force and cannot be
+//     met again (reference simulation.c:181, :191, :207, :215);
+//   * k_integrate_thread<A>: ONE THREAD PER TRAJECTORY, the a == A active particles
+//     entirely in registers, all loops unrolled, no shared memory, no shuffles: the
+//     all-pairs loop runs in the reference's (j,k) order so forces accumulate in the
+//     same order.  It advances a trajectory by up to `segment` steps and stops early
+//     the moment any pair comes within icd_dist;
+//   * that step (rare) is completed by k_resolve_and_bin, which runs the reference's
+//     greedy order-dependent meeting sweep (Q3), freezes particles, evaluates the
+//     termination rule (Q4) and sorts live trajectories into bins by active count for
+//     the next pass;
+//   * trajectories with more than THREAD_MAX_A active particles go to a wider kernel.
+#pragma once
+
+#include "heroam_device.cuh"
+
+namespace heroam {
+
+constexpr int THREAD_MAX_A = 8;   // bins 1..8: k_integrate_thread<A>, one thread per trajectory
+constexpr int BIN_WARP1 = 9;      // 9..32 active: k_integrate_warp<1>, one warp per trajectory
+constexpr int BIN_WARP2 = 10;     // 33..64 active: k_integrate_warp<2> (two particles per lane)
+constexpr int BIN_WARP4 = 11;     // 65..128 active: k_integrate_warp<4>
+constexpr int N_BINS = 12;
+constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
+constexpr int INTEGRATE_TPB = 128;
+constexpr int WARP_KERNEL_WARPS = 4;  // warps (= trajectories) per block of k_integrate_warp
+
+__host__ __device__ inline int bin_of(uint32_t active) {
+  if (active <= (uint32_t)THREAD_MAX_A) return (int)active;
+  if (active <= 32u) return BIN_WARP1;
+  if (active <= 64u) return BIN_WARP2;
+  return BIN_WARP4;
+}
+
+__device__ __forceinline__ void ld3(const float *src, float dst[3]) {
+  dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+}
+__device__ __forceinline__ void st3(float *dst, const float src[3]) {
+  dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------
+// k_prepare: imported records -> working state.  time := 0 (Q1); frozen-at-import
+// particles get the zero force the first calculate_force call would give them
+// (simulation.c:170-176).
+// ---------------------------------------------------------------------------------
+__global__ void k_prepare(DevView v, const uint32_t *__restrict__ first,
+                          const uint32_t *__restrict__ counts) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= v.n_traj) return;
+  TrajMeta m;
+  m.first = first[t];
+  m.no = counts[t];
+  m.steps = 0;
+  m.time = 0.0f;
+  m.n_flagged = 0;
+  for (uint32_t j = 0; j < m.no; ++j) {
+    heroam_particle *p = v.particles + m.first + j;
+    p->time = 0.0f;
+    if (p->success) {
+      p->success = 1;
+      ++m.n_flagged;
+      if (v.c.max_steps > 0) {
+        p->force[0] = 0.0f; p->force[1] = 0.0f; p->force[2] = 0.0f;
+        p->force_mag = 0.0f;
+      }
+    }
+  }
+  m.n_active = m.no - m.n_flagged;
+  m.status = ST_LIVE;
+  m.step_stop = 0;
+  v.meta[t] = m;
+}
+
+// ---------------------------------------------------------------------------------
+// finish_step: complete a step that k_integrate_* abandoned after the drift because a
+// pair came within icd_dist.  Record format on entry (per active particle):
+//   orientation, position : after the drift            ang_velocity : w(t)  (pre-step)
+//   velocity, velocity_sq : r(t) x w(t) and its square (or the imported values if the
+//                           trajectory has not completed a step yet)
+//   force                 : scratch, holds w(t + dt/2)   time : t
+// Does calculate_force (simulation.c:158-236) and the second half of the step
+// (:496-509) straight on the records, in the reference's order.
+// ---------------------------------------------------------------------------------
+template <class P>
+__device__ void finish_step(const DevView &v, TrajMeta &m, Counters &work) {
+  const Consts &c = v.c;
+  heroam_particle *base = v.particles + m.first;
+  const uint32_t *act = v.act + m.first;
+  const uint32_t a = m.n_active;
+  // pass 1: greedy meeting sweep (:178-202)
+  for (uint32_t js = 0; js < a; ++js) {
+    heroam_particle *pj = base + act[js];
+    if (pj->success) continue;
+    for (uint32_t ks = js + 1; ks < a; ++ks) {
+      heroam_particle *pk = base + act[ks];
+      if (pk->success) continue;
+      if (pair_dist_sq<P>(pj->position, pk->position) < c.icd2) {
+        pj->success = 1;
+        pk->success = 1;
+      }
+    }
+  }
+  // survivors: w(t+dt/2) moves from the scratch slot to ang_velocity; everybody's force := 0
+  uint32_t remaining = 0;
+  for (uint32_t s = 0; s < a; ++s) {
+    heroam_particle *p = base + act[s];
+    if (!p->success) {
+      ++remaining;
+      p->ang_velocity[0] = p->force[0];
+      p->ang_velocity[1] = p->force[1];
+      p->ang_velocity[2] = p->force[2];
+    }
+    p->force[0] = 0.0f; p->force[1] = 0.0f; p->force[2] = 0.0f;
+    p->force_mag = 0.0f;
+  }
+  // pass 2: forces among the survivors (:205-233)
+  uint32_t inrange = 0, pairs = 0;
+  for (uint32_t js = 0; js < a; ++js) {
+    heroam_particle *pj = base + act[js];
+    if (pj->success) continue;
+    if (act[js] + 1u >= m.no) continue;  // the loop bound j < no - 1
+    for (uint32_t ks = js + 1; ks < a; ++ks) {
+      heroam_particle *pk = base + act[ks];
+      if (pk->success) continue;
+      ++pairs;
+      float fj[3], fk[3];
+      ld3(pj->force, fj);
+      ld3(pk->force, fk);
+      pair_force<P>(c, v.table, pj->position, pk->position, fj, fk, inrange);
+      st3(pj->force, fj);
+      st3(pk->force, fk);
+    }
+    pj->force_mag = vec_norm(pj->force);
+  }
+  // second kick, stored velocity, clock (:496-509)
+  const float t_next = __fadd_rn(m.time, c.dt);
+  for (uint32_t s = 0; s < a; ++s) {
+    heroam_particle *p = base + act[s];
+    if (p->success) continue;
+    float hk[3], w[3], vel[3], v2;
+    half_kick<P>(c, p->position, p->force, hk);
+    w[0] = P::add(p->ang_velocity[0], hk[0]);
+    w[1] = P::add(p->ang_velocity[1], hk[1]);
+    w[2] = P::add(p->ang_velocity[2], hk[2]);
+    st3(p->ang_velocity, w);
+    stored_velocity<P>(p->position, w, vel, v2);
+    st3(p->velocity, vel);
+    p->velocity_sq = v2;
+    p->time = t_next;
+  }
+  m.n_flagged += a - remaining;
+  m.n_active = remaining;
+  m.steps += 1;
+  if (remaining > 0) m.time = t_next;  // :512-517, max over particle clocks
+  m.status = ST_LIVE;
+  work.particle_steps += remaining;
+  work.pair_steps += pairs;
+  work.inrange_steps += inrange;
+}
+
+// ---------------------------------------------------------------------------------
+// k_resolve_and_bin: one thread per trajectory, once per pass.
+//   1. finish a pending meeting step;
+//   2. evaluate the loop condition `!success && time < max_time` (simulation.c:469)
+//      plus the defined exits (deadlock, step cap);
+//   3. list the active particles and append the trajectory to the bin of its
+//      active count with the step at which the next segment ends.
+// ---------------------------------------------------------------------------------
+template <class P>
+__global__ void k_resolve_and_bin(DevView v, uint32_t segment, uint32_t step_cap,
+                                  uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  Counters work = {0, 0, 0, 0};
+  int bin = -1;
+  if (t < v.n_traj) {
+    TrajMeta m = v.meta[t];
+    if (m.status < ST_DONE) {
+      const Consts &c = v.c;
+      if (m.status == ST_MIDSTEP) finish_step<P>(v, m, work);
+      uint32_t done = 0xffffffffu;
+      if (m.steps == 0) {
+        if (!(0.0f < c.max_time)) {
+          done = HEROAM_DONE_MAXTIME;  // the reference's loop body never runs
+        } else if (step_cap == 0u) {
+          done = HEROAM_DONE_STEPCAP;
+        } else if (m.n_active == 0) {
+          // a step with nobody to move: forces are zeroed (k_prepare), no clock advances
+          m.steps = 1;
+          done = all_paired(m.no, m.n_flagged) ? HEROAM_DONE_SUCCESS : HEROAM_DONE_DEADLOCK;
+        }
+      } else if (all_paired(m.no, m.n_flagged)) {
+        done = HEROAM_DONE_SUCCESS;
+      } else if (!(m.time < c.max_time)) {
+        done = HEROAM_DONE_MAXTIME;
+      } else if (m.n_active == 0) {
+        done = HEROAM_DONE_DEADLOCK;
+      } else if (m.steps >= step_cap) {
+        done = HEROAM_DONE_STEPCAP;
+      }
+      if (done == 0xffffffffu && m.n_active > (uint32_t)MAX_ACTIVE) {
+        done = HEROAM_DONE_UNSUPPORTED;
+        atomicAdd(&v.counters->unsupported, 1ull);
+      }
+      if (done != 0xffffffffu) {
+        m.status = ST_DONE + done;
+      } else {
+        uint32_t s = 0;
+        for (uint32_t j = 0; j < m.no; ++j)
+          if (!v.particles[m.first + j].success) v.act[m.first + s++] = j;
+        uint32_t stop = m.steps + segment;
+        if (stop < m.steps) stop = 0xffffffffu;
+        // the criterion already holds before the first step: the reference still runs
+        // exactly one iteration (do-while shape of :466-469, Q2)
+        if (m.steps == 0 && all_paired(m.no, m.n_flagged)) stop = 1;
+        if (stop > c.max_steps) stop = c.max_steps;
+        if (stop > step_cap) stop = step_cap;
+        m.step_stop = stop;
+        bin = bin_of(m.n_active);
+      }
+      v.meta[t] = m;
+    }
+  }
+  // warp-aggregated append: one atomic per (warp, bin)
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (bin >= 0) {
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(bin_count + bin, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    bin_list[(size_t)bin * v.n_traj + base + rank] = t;
+  }
+  const unsigned long long ps = warp_sum_u64(work.particle_steps);
+  const unsigned long long pr = warp_sum_u64(work.pair_steps);
+  const unsigned long long ir = warp_sum_u64(work.inrange_steps);
+  if (lane == 0 && (ps | pr | ir)) {
+    atomicAdd(&v.counters->particle_steps, ps);
+    atomicAdd(&v.counters->pair_steps, pr);
+    atomicAdd(&v.counters->inrange_steps, ir);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_integrate_thread<A>: one thread per trajectory, A active particles in registers.
+// ---------------------------------------------------------------------------------
+template <int A, class P>
+__global__ void __launch_bounds__(INTEGRATE_TPB)
+k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long done_steps = 0, inrange_total = 0;
+  if (item < count) {
+    const Consts &c = v.c;
+    const uint32_t t = list[item];
+    TrajMeta m = v.meta[t];
+    heroam_particle *rec[A];
+    float q[A][4], w[A][3], r[A][3], f[A][3], hk[A][3], wh[A][3], r_old[A][3];
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      rec[s] = v.particles + m.first + v.act[m.first + s];
+      const heroam_particle *p = rec[s];
+      q[s][0] = p->orientation[0]; q[s][1] = p->orientation[1];
+      q[s][2] = p->orientation[2]; q[s][3] = p->orientation[3];
+      ld3(p->position, r[s]);
+      ld3(p->ang_velocity, w[s]);
+      ld3(p->force, f[s]);
+      half_kick<P>(c, r[s], f[s], hk[s]);
+    }
+    uint32_t steps = m.steps;
+    float time = m.time;
+    bool met = false;
+    while (steps < m.step_stop) {
+      // first half kick + drift (simulation.c:478-490)
+#pragma unroll
+      for (int s = 0; s < A; ++s) {
+        r_old[s][0] = r[s][0]; r_old[s][1] = r[s][1]; r_old[s][2] = r[s][2];
+        wh[s][0] = P::add(w[s][0], hk[s][0]);
+        wh[s][1] = P::add(w[s][1], hk[s][1]);
+        wh[s][2] = P::add(w[s][2], hk[s][2]);
+        drift<P>(c, wh[s], q[s], r[s]);
+        f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
+      }
+      // all pairs in the reference's (j,k) order (:178-233)
+      // Branch-free and staged row by row: geometry and gathers of a whole row are
+      // issued before any of them is consumed.
+      float dmin = 3.0e38f;
+      uint32_t in_step = 0;
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) {
+        PairGeom g[A];
+        float tv[A];
+#pragma unroll
+        for (int k = j + 1; k < A; ++k) {
+          g[k] = pair_geom<P>(c, r[j], r[k]);
+          tv[k] = pair_gather(v.table, g[k]);
+          dmin = fminf(dmin, g[k].d);
+          in_step += g[k].inside ? 1u : 0u;
+        }
+#pragma unroll
+        for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
+      }
+      if (dmin < c.icd2) { met = true; break; }
+      // second half kick (:496-509); velocity and clock fields are written at the end
+#pragma unroll
+      for (int s = 0; s < A; ++s) {
+        half_kick<P>(c, r[s], f[s], hk[s]);
+        w[s][0] = P::add(wh[s][0], hk[s][0]);
+        w[s][1] = P::add(wh[s][1], hk[s][1]);
+        w[s][2] = P::add(wh[s][2], hk[s][2]);
+      }
+      time = __fadd_rn(time, c.dt);
+      ++steps;
+      inrange_total += in_step;
+    }
+    done_steps = steps - m.steps;
+    if (met) {
+      // hand the half-done step to k_resolve_and_bin (format: see finish_step)
+#pragma unroll
+      for (int s = 0; s < A; ++s) {
+        heroam_particle *p = rec[s];
+        p->orientation[0] = q[s][0]; p->orientation[1] = q[s][1];
+        p->orientation[2] = q[s][2]; p->orientation[3] = q[s][3];
+        st3(p->position, r[s]);
+        st3(p->ang_velocity, w[s]);
+        st3(p->force, wh[s]);
+        p->time = time;
+        if (steps > 0) {
+          float vel[3], v2;
+          stored_velocity<P>(r_old[s], w[s], vel, v2);
+          st3(p->velocity, vel);
+          p->velocity_sq = v2;
+        }
+      }
+      m.status = ST_MIDSTEP;
+    } else if (done_steps > 0) {
+      // clean state at a step boundary, every field as the reference holds it
+#pragma unroll
+      for (int s = 0; s < A; ++s) {
+        heroam_particle *p = rec[s];
+        p->orientation[0] = q[s][0]; p->orientation[1] = q[s][1];
+        p->orientation[2] = q[s][2]; p->orientation[3] = q[s][3];
+        st3(p->position, r[s]);
+        st3(p->ang_velocity, w[s]);
+        st3(p->force, f[s]);
+        float vel[3], v2;
+        stored_velocity<P>(r[s], w[s], vel, v2);
+        st3(p->velocity, vel);
+        p->velocity_sq = v2;
+        p->time = time;
+        // force_mag only exists for indices below no - 1 (:205, :232; Q9)
+        const uint32_t j = (uint32_t)(p - (v.particles + m.first));
+        p->force_mag = (j + 1u < m.no) ? vec_norm(f[s]) : 0.0f;
+      }
+    }
+    m.steps = steps;
+    m.time = time;
+    v.meta[t] = m;
+  }
+  const unsigned long long ds = warp_sum_u64(done_steps);
+  const unsigned long long ir = warp_sum_u64(inrange_total);
+  if ((threadIdx.x & 31u) == 0 && ds) {
+    atomicAdd(&v.counters->particle_steps, ds * A);
+    atomicAdd(&v.counters->pair_steps, ds * (A * (A - 1) / 2));
+    atomicAdd(&v.counters->inrange_steps, ir);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_integrate_warp<PPL>: one warp per trajectory, up to 32*PPL active particles; lane l
+// owns active particles l, l+32, ...  Post-drift positions are staged in shared memory
+// (16 B per particle, broadcast reads).  Every lane accumulates the force on ITS particle
+// over all partners in ascending partner order, which is exactly the order in which the
+// reference's (j,k) double loop touches that particle (first the F_k -= f of every j < k,
+// then the F_j += f of every k > j, simulation.c:205-231); since -(a-b) == (b-a) and
+// s*(-x) == -(s*x) in IEEE arithmetic the result has the reference's bits without any
+// cross-lane reduction.  Each pair is therefore evaluated by both of its lanes.
+// ---------------------------------------------------------------------------------
+template <int PPL, class P>
+__global__ void __launch_bounds__(32 * WARP_KERNEL_WARPS)
+k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
+  __shared__ float4 s_pos[WARP_KERNEL_WARPS][32 * PPL];
+  const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t item = blockIdx.x * WARP_KERNEL_WARPS + wib;
+  if (item >= count) return;  // whole warp leaves together
+  const Consts &c = v.c;
+  const uint32_t t = list[item];
+  TrajMeta m = v.meta[t];
+  const uint32_t a = m.n_active;
+  float4 *pos = s_pos[wib];
+  heroam_particle *rec[PPL];
+  bool own[PPL];
+  float q[PPL][4], w[PPL][3], r[PPL][3], f[PPL][3], hk[PPL][3], wh[PPL][3], r_old[PPL][3];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const uint32_t s = lane + 32u * i;
+    own[i] = s < a;
+    rec[i] = v.particles + m.first + (own[i] ? v.act[m.first + s] : 0u);
+    if (own[i]) {
+      const heroam_particle *p = rec[i];
+      q[i][0] = p->orientation[0]; q[i][1] = p->orientation[1];
+      q[i][2] = p->orientation[2]; q[i][3] = p->orientation[3];
+      ld3(p->position, r[i]);
+      ld3(p->ang_velocity, w[i]);
+      ld3(p->force, f[i]);
+      half_kick<P>(c, r[i], f[i], hk[i]);
+    } else {
+      q[i][0] = 1.0f; q[i][1] = q[i][2] = q[i][3] = 0.0f;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { r[i][d] = 0.0f; w[i][d] = 0.0f; f[i][d] = 0.0f; hk[i][d] = 0.0f; }
+    }
+  }
+  uint32_t steps = m.steps;
+  float time = m.time;
+  bool met = false;
+  unsigned long long inrange_total = 0;
+  while (steps < m.step_stop) {
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      if (own[i]) {
+        r_old[i][0] = r[i][0]; r_old[i][1] = r[i][1]; r_old[i][2] = r[i][2];
+        wh[i][0] = P::add(w[i][0], hk[i][0]);
+        wh[i][1] = P::add(w[i][1], hk[i][1]);
+        wh[i][2] = P::add(w[i][2], hk[i][2]);
+        drift<P>(c, wh[i], q[i], r[i]);
+        pos[lane + 32u * i] = make_float4(r[i][0], r[i][1], r[i][2], 0.0f);
+      }
+      f[i][0] = 0.0f; f[i][1] = 0.0f; f[i][2] = 0.0f;
+    }
+    __syncwarp();
+    float dmin = 3.0e38f;
+    uint32_t in_step = 0;
+    // partners in ascending order, four at a time: geometry and gathers first, then the
+    // (ordered) accumulation; everything branch-free, invalid slots contribute zero
+    constexpr int UNR = 4;
+    for (uint32_t p0 = 0; p0 < a; p0 += UNR) {
+      PairGeom g[UNR][PPL];
+      float tv[UNR][PPL];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const uint32_t p = p0 + u;
+        const float4 rp4 = pos[p < a ? p : a - 1u];
+        const float rp[3] = {rp4.x, rp4.y, rp4.z};
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          const uint32_t s = lane + 32u * i;
+          const bool valid = own[i] && p < a && s != p;
+          g[u][i] = pair_geom<P>(c, r[i], rp);  // own particle first: sign of (r_s - r_p)
+          g[u][i].inside = g[u][i].inside && valid;
+          g[u][i].bin = g[u][i].inside ? g[u][i].bin : 0;
+          tv[u][i] = pair_gather(v.table, g[u][i]);
+          dmin = fminf(dmin, valid ? g[u][i].d : 3.0e38f);
+          in_step += (g[u][i].inside && s < p) ? 1u : 0u;  // count each pair once
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          // a masked slot may have d == 0 (the particle itself): keep sqrt away from it
+          const float dsafe = g[u][i].inside ? g[u][i].d : 1.0f;
+          pair_apply_own<P>(pair_scale<P>(tv[u][i], dsafe), g[u][i], f[i]);
+        }
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, dmin < c.icd2)) { met = true; break; }
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      if (own[i]) {
+        half_kick<P>(c, r[i], f[i], hk[i]);
+        w[i][0] = P::add(wh[i][0], hk[i][0]);
+        w[i][1] = P::add(wh[i][1], hk[i][1]);
+        w[i][2] = P::add(wh[i][2], hk[i][2]);
+      }
+    }
+    time = __fadd_rn(time, c.dt);
+    ++steps;
+    inrange_total += in_step;
+  }
+  const unsigned long long done_steps = steps - m.steps;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    if (!own[i]) continue;
+    heroam_particle *p = rec[i];
+    if (met) {
+      p->orientation[0] = q[i][0]; p->orientation[1] = q[i][1];
+      p->orientation[2] = q[i][2]; p->orientation[3] = q[i][3];
+      st3(p->position, r[i]);
+      st3(p->ang_velocity, w[i]);
+      st3(p->force, wh[i]);
+      p->time = time;
+      if (steps > 0) {
+        float vel[3], v2;
+        stored_velocity<P>(r_old[i], w[i], vel, v2);
+        st3(p->velocity, vel);
+        p->velocity_sq = v2;
+      }
+    } else if (done_steps > 0) {
+      p->orientation[0] = q[i][0]; p->orientation[1] = q[i][1];
+      p->orientation[2] = q[i][2]; p->orientation[3] = q[i][3];
+      st3(p->position, r[i]);
+      st3(p->ang_velocity, w[i]);
+      st3(p->force, f[i]);
+      float vel[3], v2;
+      stored_velocity<P>(r[i], w[i], vel, v2);
+      st3(p->velocity, vel);
+      p->velocity_sq = v2;
+      p->time = time;
+      const uint32_t j = (uint32_t)(p - (v.particles + m.first));
+      p->force_mag = (j + 1u < m.no) ? vec_norm(f[i]) : 0.0f;
+    }
+  }
+  const unsigned long long ir = warp_sum_u64(inrange_total);
+  if (lane == 0) {
+    if (met) m.status = ST_MIDSTEP;
+    m.steps = steps;
+    m.time = time;
+    v.meta[t] = m;
+    if (done_steps) {
+      atomicAdd(&v.counters->particle_steps, done_steps * a);
+      atomicAdd(&v.counters->pair_steps, done_steps * ((unsigned long long)a * (a - 1) / 2));
+      atomicAdd(&v.counters->inrange_steps, ir);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_integrate_records: any active count, one thread per trajectory, state left in the
+// global records (slow; the correctness anchor for the wide kernels).
+// ---------------------------------------------------------------------------------
+template <class P>
+__global__ void k_integrate_records(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= count) return;
+  const Consts &c = v.c;
+  const uint32_t t = list[item];
+  TrajMeta m = v.meta[t];
+  heroam_particle *base = v.particles + m.first;
+  const uint32_t *act = v.act + m.first;
+  const uint32_t a = m.n_active;
+  unsigned long long done_steps = 0, inrange_total = 0;
+  while (m.steps < m.step_stop) {
+    for (uint32_t s = 0; s < a; ++s) {
+      heroam_particle *p = base + act[s];
+      float hk[3], wh[3], q[4], r[3];
+      half_kick<P>(c, p->position, p->force, hk);
+      wh[0] = P::add(p->ang_velocity[0], hk[0]);
+      wh[1] = P::add(p->ang_velocity[1], hk[1]);
+      wh[2] = P::add(p->ang_velocity[2], hk[2]);
+      q[0] = p->orientation[0]; q[1] = p->orientation[1]; q[2] = p->orientation[2]; q[3] = p->orientation[3];
+      drift<P>(c, wh, q, r);
+      p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
+      st3(p->position, r);
+      st3(p->force, wh);  // scratch slot: w(t + dt/2)
+    }
+    bool met = false;
+    for (uint32_t js = 0; js < a && !met; ++js)
+      for (uint32_t ks = js + 1; ks < a; ++ks)
+        if (pair_dist_sq<P>(base[act[js]].position, base[act[ks]].position) < c.icd2) { met = true; break; }
+    if (met) { m.status = ST_MIDSTEP; break; }
+    for (uint32_t s = 0; s < a; ++s) {
+      heroam_particle *p = base + act[s];
+      st3(p->velocity, p->force);  // keep w(t + dt/2) while the forces are rebuilt
+      p->force[0] = 0.0f; p->force[1] = 0.0f; p->force[2] = 0.0f;
+    }
+    uint32_t in_step = 0;
+    for (uint32_t js = 0; js + 1 < a; ++js) {
+      heroam_particle *pj = base + act[js];
+      for (uint32_t ks = js + 1; ks < a; ++ks) {
+        heroam_particle *pk = base + act[ks];
+        float fj[3], fk[3];
+        ld3(pj->force, fj);
+        ld3(pk->force, fk);
+        pair_force<P>(c, v.table, pj->position, pk->position, fj, fk, in_step);
+        st3(pj->force, fj);
+        st3(pk->force, fk);
+      }
+    }
+    m.time = __fadd_rn(m.time, c.dt);
+    for (uint32_t s = 0; s < a; ++s) {
+      heroam_particle *p = base + act[s];
+      float hk[3], w[3], vel[3], v2;
+      half_kick<P>(c, p->position, p->force, hk);
+      w[0] = P::add(p->velocity[0], hk[0]);
+      w[1] = P::add(p->velocity[1], hk[1]);
+      w[2] = P::add(p->velocity[2], hk[2]);
+      st3(p->ang_velocity, w);
+      stored_velocity<P>(p->position, w, vel, v2);
+      st3(p->velocity, vel);
+      p->velocity_sq = v2;
+      p->time = m.time;
+      p->force_mag = (act[s] + 1u < m.no) ? vec_norm(p->force) : 0.0f;
+    }
+    ++m.steps;
+    ++done_steps;
+    inrange_total += in_step;
+  }
+  v.meta[t] = m;
+  if (done_steps) {
+    atomicAdd(&v.counters->particle_steps, done_steps * a);
+    atomicAdd(&v.counters->pair_steps, done_steps * ((unsigned long long)a * (a - 1) / 2));
+    atomicAdd(&v.counters->inrange_steps, inrange_total);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_results: per-trajectory outcome for the host
+// ---------------------------------------------------------------------------------
+__global__ void k_results(DevView v, heroam_traj_result *__restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= v.n_traj) return;
+  const TrajMeta m = v.meta[t];
+  heroam_traj_result r;
+  r.steps = m.steps;
+  r.status = m.status >= ST_DONE ? m.status - ST_DONE : 0xffffffffu;
+  r.n_flagged = m.n_flagged;
+  r.time = m.time;
+  out[t] = r;
+}
+
+// ---------------------------------------------------------------------------------
+// k_fma_peak: register-resident FFMA chains, 8 independent accumulators per thread.
+// The measured FP32 ceiling that roofline fractions are quoted against.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678f) out[0] = s;  // never true in practice; keeps the chains alive
+}
+
+}  // namespace heroam

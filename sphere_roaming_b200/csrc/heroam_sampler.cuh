@@ -1,0 +1,428 @@
+// heroam_sampler.cuh -- Philox sampling stage and fused statistics (included by heroam_gpu.cu).
+//
+// The sampling stage restates initialize_particles (reference simulation.c:277-337 with
+// :238-275 and vector.c:74-134) with the libc rand() stream replaced by a counter-based
+// Philox4x32-10 stream per trajectory: key = (seed, he_number high word), counter =
+// (block, trajectory index, he_number low word).  Each 32-bit output is shifted to the 31
+// bits of glibc's rand() and then goes through the reference's own conversions, so the
+// arithmetic downstream of the integer draw is the reference's.  oracle/heroam_oracle.c
+// (orc_sample, source = 1) is the CPU twin of this file.
+#pragma once
+
+namespace heroam {
+
+struct Philox {
+  uint32_t key0, key1, c1, c2, c3;
+  uint32_t block;   // next block number (counter word 0)
+  uint32_t buf[4];
+  int have;
+
+  __device__ __forceinline__ void begin(long long seed, unsigned long long he_number, unsigned long long traj) {
+    key0 = (uint32_t)((unsigned long long)seed & 0xffffffffu);
+    key1 = (uint32_t)((unsigned long long)seed >> 32) ^ (uint32_t)(he_number >> 32);
+    c1 = (uint32_t)(traj & 0xffffffffu);
+    c2 = (uint32_t)(traj >> 32);
+    c3 = (uint32_t)(he_number & 0xffffffffu);
+    block = 0;
+    have = 0;
+  }
+  __device__ __forceinline__ void refill() {
+    uint32_t x0 = block, x1 = c1, x2 = c2, x3 = c3, k0 = key0, k1 = key1;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+      const uint32_t n0 = hi1 ^ x1 ^ k0, n2 = hi0 ^ x3 ^ k1;
+      x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
+    ++block;
+    have = 4;
+  }
+  // 31-bit integer with the range of glibc rand()
+  __device__ __forceinline__ int next() {
+    if (have == 0) refill();
+    const uint32_t word = have == 4 ? buf[0] : have == 3 ? buf[1] : have == 2 ? buf[2] : buf[3];
+    --have;
+    return (int)(word >> 1);
+  }
+  // resume after `consumed` draws
+  __device__ __forceinline__ void skip_to(uint32_t consumed) {
+    block = consumed >> 2;
+    have = 0;
+    const int within = (int)(consumed & 3u);
+    if (within) {
+      refill();
+      have = 4 - within;
+    }
+  }
+  __device__ __forceinline__ uint32_t consumed() const { return block * 4u - (uint32_t)have; }
+};
+
+// (float)rand() / RAND_MAX: int -> float, RAND_MAX -> float (2^31), float divide
+__device__ __forceinline__ float unit_f(Philox &g) { return __fdiv_rn(__int2float_rn(g.next()), 2147483648.0f); }
+// draws that feed a logarithm come from (0,1] (the reference can feed 0, simulation.c:249-251)
+__device__ __forceinline__ float unit_f_pos(Philox &g) {
+  int r = g.next();
+  if (r == 0) r = 1;
+  return __fdiv_rn(__int2float_rn(r), 2147483648.0f);
+}
+
+// zero-truncated Poisson by Knuth's product of uniforms (simulation.c:257-275, :302-304)
+__device__ inline uint32_t sample_count(Philox &g, double limit) {
+  int n;
+  do {
+    n = 0;
+    double p = 1.0;
+    do {
+      ++n;
+      const double u = __ddiv_rn((double)g.next(), 2147483647.0);
+      p = __dmul_rn(p, u);
+    } while (p > limit);
+    --n;
+  } while (n < 1);
+  return (uint32_t)n;
+}
+
+// q (0,0,1) q^-1 exactly as the reference evaluates it (vector.c:94-110, :182-205)
+__device__ inline void pole_image_exact(const float q[4], float out[3]) {
+  typedef Exact P;
+  const float n2 = P::dot4(q[0], q[1], q[2], q[3]);
+  const float ia = __fdiv_rn(q[0], n2), ix = -__fdiv_rn(q[1], n2), iy = -__fdiv_rn(q[2], n2), iz = -__fdiv_rn(q[3], n2);
+  const float ua = -q[3], ux = q[2], uy = -q[1], uz = q[0];
+  out[0] = P::sub(P::add(P::add(P::mul(ua, ix), P::mul(ux, ia)), P::mul(uy, iz)), P::mul(uz, iy));
+  out[1] = P::add(P::add(P::sub(P::mul(ua, iy), P::mul(ux, iz)), P::mul(uy, ia)), P::mul(uz, ix));
+  out[2] = P::add(P::sub(P::add(P::mul(ua, iz), P::mul(ux, iy)), P::mul(uy, ix)), P::mul(uz, ia));
+}
+
+// Marsaglia (1972) point on S^3 (vector.c:112-134)
+__device__ inline void sample_orientation(Philox &g, float q[4]) {
+  float x, y, z, u, v, w;
+  do {
+    x = __fsub_rn(__fmul_rn(2.0f, unit_f(g)), 1.0f);
+    y = __fsub_rn(__fmul_rn(2.0f, unit_f(g)), 1.0f);
+    z = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+  } while (z > 1.0f);
+  do {
+    u = __fsub_rn(__fmul_rn(2.0f, unit_f(g)), 1.0f);
+    v = __fsub_rn(__fmul_rn(2.0f, unit_f(g)), 1.0f);
+    w = __fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v));
+  } while (w > 1.0f);
+  const float sc = __fsqrt_rn(__fdiv_rn(__fsub_rn(1.0f, z), w));
+  q[0] = x; q[1] = y; q[2] = __fmul_rn(sc, u); q[3] = __fmul_rn(sc, v);
+  const float mag = __fsqrt_rn(Exact::dot4(q[0], q[1], q[2], q[3]));
+  q[0] = __fdiv_rn(q[0], mag); q[1] = __fdiv_rn(q[1], mag);
+  q[2] = __fdiv_rn(q[2], mag); q[3] = __fdiv_rn(q[3], mag);
+}
+
+// sigma * chi_3 through Box-Muller in double, as simulation.c:238-255
+__device__ inline float sample_speed(Philox &g, float sigma) {
+  const double pi = (double)3.14159274101257324f;  // float pi = 4*atan(1)
+  const float u1 = unit_f_pos(g), u2 = unit_f(g), u3 = unit_f_pos(g), u4 = unit_f(g);
+  const double r1 = sqrt(-2.0 * log((double)u1)), a1 = 2.0 * pi * (double)u2;
+  const double r3 = sqrt(-2.0 * log((double)u3)), a3 = 2.0 * pi * (double)u4;
+  const float z1 = (float)(r1 * cos(a1));
+  const float z2 = (float)(r1 * sin(a1));
+  const float z3 = (float)(r3 * cos(a3));
+  return (float)(sqrt((double)Exact::dot3(z1, z2, z3)) * (double)sigma);
+}
+
+struct SampleParams {
+  long long seed;
+  unsigned long long he_number;
+  unsigned long long first_index;
+  double limit;        // exp(-lambda), host libm (simulation.c:263)
+  double radius_init;  // 2.22 * pow((double)N, 1/3), double (simulation.c:297)
+  float sigma;         // conf->velocity
+};
+
+// stage 1: excitation count per trajectory and how many draws it consumed
+__global__ void k_sample_counts(SampleParams sp, uint32_t n_traj, uint32_t *__restrict__ counts,
+                                uint32_t *__restrict__ consumed) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_traj) return;
+  Philox g;
+  g.begin(sp.seed, sp.he_number, sp.first_index + t);
+  counts[t] = sample_count(g, sp.limit);
+  consumed[t] = g.consumed();
+}
+
+// calculate_force on a freshly sampled trajectory (simulation.c:334, :158-236)
+__device__ inline void initial_forces(const Consts &c, const float *__restrict__ table, heroam_particle *p, uint32_t n) {
+  for (uint32_t j = 0; j < n; ++j) {
+    if (p[j].success) continue;  // checked once per j: a freshly flagged j keeps scanning (Q3)
+    for (uint32_t k = j + 1; k < n; ++k) {
+      if (p[k].success) continue;
+      if (pair_dist_sq<Exact>(p[j].position, p[k].position) < c.icd2) { p[j].success = 1; p[k].success = 1; }
+    }
+  }
+  uint32_t unused = 0;
+  for (uint32_t j = 0; j + 1 < n; ++j) {
+    if (p[j].success) continue;
+    for (uint32_t k = j + 1; k < n; ++k) {
+      if (p[k].success) continue;
+      float fj[3], fk[3];
+      ld3(p[j].force, fj);
+      ld3(p[k].force, fk);
+      pair_force<Exact>(c, table, p[j].position, p[k].position, fj, fk, unused);
+      st3(p[j].force, fj);
+      st3(p[k].force, fk);
+    }
+    p[j].force_mag = vec_norm(p[j].force);
+  }
+}
+
+// stage 2: the particles of every trajectory (serial within a trajectory: one stream)
+__global__ void k_sample_particles(SampleParams sp, Consts c, const float *__restrict__ table, uint32_t n_traj,
+                                   const uint32_t *__restrict__ counts, const uint32_t *__restrict__ first,
+                                   const uint32_t *__restrict__ consumed, heroam_particle *__restrict__ particles) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_traj) return;
+  Philox g;
+  g.begin(sp.seed, sp.he_number, sp.first_index + t);
+  g.skip_to(consumed[t]);
+  const uint32_t n = counts[t];
+  heroam_particle *p = particles + first[t];
+  const float radius_f = (float)sp.radius_init;
+  for (uint32_t j = 0; j < n; ++j) {
+    heroam_particle out;
+    out.index = j;
+    out.success = 0;
+    out.time = 0.0f;  // Q1
+    out.force_mag = 0.0f;
+    sample_orientation(g, out.orientation);
+    float unit[3];
+    pole_image_exact(out.orientation, unit);
+    out.position[0] = __fmul_rn(unit[0], radius_f);
+    out.position[1] = __fmul_rn(unit[1], radius_f);
+    out.position[2] = __fmul_rn(unit[2], radius_f);
+    const float vel = (float)((double)sample_speed(g, sp.sigma) * 1E-5);  // m/s -> A/fs (:323)
+    const float ang_vel = (float)((double)vel / sp.radius_init);           // :324
+    out.velocity_sq = __fmul_rn(vel, vel);
+    // create_perpend_vector (vector.c:74-92): a x r, a = (-y, x, 0) away from the poles
+    float a[3];
+    if (out.position[0] != 0.0f || out.position[1] != 0.0f) { a[0] = -out.position[1]; a[1] = out.position[0]; a[2] = 0.0f; }
+    else { a[0] = 0.0f; a[1] = -out.position[2]; a[2] = out.position[1]; }
+    float tan[3], tan2;
+    stored_velocity<Exact>(a, out.position, tan, tan2);  // plain cross product
+    const float k = __fdiv_rn(ang_vel, __fsqrt_rn(tan2));
+    out.ang_velocity[0] = __fmul_rn(tan[0], k);
+    out.ang_velocity[1] = __fmul_rn(tan[1], k);
+    out.ang_velocity[2] = __fmul_rn(tan[2], k);
+    float v2;
+    stored_velocity<Exact>(out.position, out.ang_velocity, out.velocity, v2);  // r x w (:329)
+    out.force[0] = 0.0f; out.force[1] = 0.0f; out.force[2] = 0.0f;
+    p[j] = out;
+  }
+  initial_forces(c, table, p, n);
+}
+
+// ---------------------------------------------------------------------------------
+// statistics of a finished batch
+// ---------------------------------------------------------------------------------
+struct DevStats {
+  unsigned long long hist_n[HEROAM_HIST_N];
+  unsigned long long hist_traj_time[HEROAM_HIST_T];
+  unsigned long long hist_meet_time[HEROAM_HIST_T];
+  unsigned long long done[8];
+  unsigned long long unmet_particles;
+  unsigned long long particles;
+  unsigned long long trajectories;
+  double sum_traj_time;
+};
+
+__device__ __forceinline__ int time_bin(float t, float max_time) {
+  int b = (int)(t / max_time * (float)HEROAM_HIST_T);
+  return b < 0 ? 0 : (b >= HEROAM_HIST_T ? HEROAM_HIST_T - 1 : b);
+}
+
+__global__ void k_stats(DevView v, DevStats *__restrict__ st) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= v.n_traj) return;
+  const TrajMeta m = v.meta[t];
+  atomicAdd(&st->hist_n[m.no < HEROAM_HIST_N ? m.no : HEROAM_HIST_N - 1], 1ull);
+  atomicAdd(&st->hist_traj_time[time_bin(m.time, v.c.max_time)], 1ull);
+  const uint32_t code = m.status >= ST_DONE ? m.status - ST_DONE : 7u;
+  atomicAdd(&st->done[code < 8u ? code : 7u], 1ull);
+  atomicAdd(&st->sum_traj_time, (double)m.time);
+  unsigned long long unmet = 0;
+  for (uint32_t j = 0; j < m.no; ++j) {
+    const heroam_particle *p = v.particles + m.first + j;
+    if (p->success) atomicAdd(&st->hist_meet_time[time_bin(p->time, v.c.max_time)], 1ull);
+    else ++unmet;
+  }
+  if (unmet) atomicAdd(&st->unmet_particles, unmet);
+  atomicAdd(&st->particles, (unsigned long long)m.no);
+  atomicAdd(&st->trajectories, 1ull);
+}
+
+}  // namespace heroam
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static double host_lambda(const heroam_config &conf, unsigned long long he_number) {
+  // simulation.c:289-293: float product and quotient first, then double
+  double lam = (double)((conf.intensity * conf.pulse_width * conf.cross_section) / conf.hv);
+  lam = (double)he_number * lam;
+  lam = 6.241509074E-06 * lam;
+  return lam;
+}
+
+// Sample `count` trajectories starting at stream index first_index into the context's
+// device buffers (they become the resident batch).  Leaves counts on the host in *h_counts
+// when requested.
+static int sample_device(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index, int count,
+                         std::vector<uint32_t> *h_counts_out) {
+  if (count < 0) return fail(HEROAM_E_ARG, "negative count");
+  CU(cudaSetDevice(ctx->device));
+  Consts c;
+  int rc = make_consts(ctx->conf, he_number, &c);
+  if (rc) return rc;
+  const double lambda = host_lambda(ctx->conf, he_number);
+  if (!(lambda > 0.0) || lambda > 700.0)
+    return fail(HEROAM_E_ARG, "mean excitation number %g outside (0, 700]: Knuth's product of uniforms "
+                "(simulation.c:257-275) is undefined there", lambda);
+  SampleParams sp;
+  sp.seed = (long long)ctx->conf.seed;
+  sp.he_number = he_number;
+  sp.first_index = first_index;
+  sp.limit = exp(-1.0 * lambda);
+  sp.radius_init = 2.22 * pow((double)he_number, 1.0 / 3.0);
+  sp.sigma = ctx->conf.velocity;
+  ctx->he_number = he_number;
+  ctx->n_traj = (uint32_t)count;
+  ctx->n_particles = 0;
+  memset(&ctx->info, 0, sizeof ctx->info);
+  if (count == 0) { ctx->uploaded = true; return HEROAM_OK; }
+  rc = reserve(ctx, (size_t)count, ctx->cap_particles ? ctx->cap_particles : 1);
+  if (rc) return rc;
+  const unsigned grid = ((unsigned)count + 127u) / 128u;
+  // the bin list is free at this point: borrow its first n words for the draw offsets
+  uint32_t *d_consumed = ctx->d_bin_list;
+  k_sample_counts<<<grid, 128, 0, ctx->main>>>(sp, (uint32_t)count, ctx->d_counts, d_consumed);
+  CU(cudaGetLastError());
+  std::vector<uint32_t> h_counts((size_t)count), h_first((size_t)count);
+  CU(cudaMemcpyAsync(h_counts.data(), ctx->d_counts, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+  CU(cudaStreamSynchronize(ctx->main));
+  size_t total = 0;
+  for (int i = 0; i < count; ++i) {
+    h_first[i] = (uint32_t)total;
+    total += h_counts[i];
+  }
+  if (total > 0xfffffff0ull) return fail(HEROAM_E_ARG, "batch too large: more than 2^32 particle records");
+  rc = reserve(ctx, (size_t)count, total);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->d_first, h_first.data(), (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->main));
+  k_sample_particles<<<grid, 128, 0, ctx->main>>>(sp, c, ctx->d_table, (uint32_t)count, ctx->d_counts, ctx->d_first,
+                                                   d_consumed, ctx->d_particles);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->main));
+  ctx->info.kernel_launches += 2;
+  ctx->n_particles = total;
+  ctx->uploaded = true;
+  if (h_counts_out) h_counts_out->swap(h_counts);
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_sample_flat(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index,
+                                      int count, uint32_t *counts, heroam_particle *flat, long capacity, long *total) {
+  if (!ctx || !counts || !total) return fail(HEROAM_E_ARG, "heroam_gpu_sample_flat: null argument");
+  std::vector<uint32_t> h_counts;
+  int rc = sample_device(ctx, he_number, first_index, count, &h_counts);
+  if (rc) return rc;
+  if (count > 0) memcpy(counts, h_counts.data(), (size_t)count * sizeof(uint32_t));
+  *total = (long)ctx->n_particles;
+  if ((long)ctx->n_particles <= capacity && flat && ctx->n_particles)
+    CU(cudaMemcpy(flat, ctx->d_particles, ctx->n_particles * sizeof(heroam_particle), cudaMemcpyDeviceToHost));
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_sample_batch(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index,
+                                       int count, heroam_particles *out) {
+  if (!ctx || (!out && count > 0)) return fail(HEROAM_E_ARG, "heroam_gpu_sample_batch: null argument");
+  std::vector<uint32_t> h_counts;
+  int rc = sample_device(ctx, he_number, first_index, count, &h_counts);
+  if (rc) return rc;
+  std::vector<heroam_particle> flat(ctx->n_particles ? ctx->n_particles : 1);
+  if (ctx->n_particles)
+    CU(cudaMemcpy(flat.data(), ctx->d_particles, ctx->n_particles * sizeof(heroam_particle), cudaMemcpyDeviceToHost));
+  size_t at = 0;
+  for (int i = 0; i < count; ++i) {
+    out[i].no = h_counts[i];
+    out[i].index = (uint32_t)(first_index + (unsigned long long)i);
+    // ownership as in the reference: the engine mallocs, the caller frees (simulation.c:310, :339-341)
+    out[i].particle = (heroam_particle *)malloc((size_t)h_counts[i] * sizeof(heroam_particle));
+    if (!out[i].particle) return fail(HEROAM_E_ARG, "out of host memory");
+    memcpy(out[i].particle, flat.data() + at, (size_t)h_counts[i] * sizeof(heroam_particle));
+    at += h_counts[i];
+  }
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index,
+                                    unsigned long long count, heroam_stats *out) {
+  if (!ctx || !out) return fail(HEROAM_E_ARG, "heroam_gpu_run_stats: null argument");
+  CU(cudaSetDevice(ctx->device));
+  memset(out, 0, sizeof *out);
+  DevStats *d_stats = nullptr;
+  CU(cudaMalloc(&d_stats, sizeof(DevStats)));
+  CU(cudaMemset(d_stats, 0, sizeof(DevStats)));
+  const unsigned long long batch_max = 1ull << 20;
+  heroam_run_info total;
+  memset(&total, 0, sizeof total);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, ctx->main));
+  int rc = HEROAM_OK;
+  for (unsigned long long done = 0; done < count && rc == HEROAM_OK; done += batch_max) {
+    const int n = (int)((count - done) < batch_max ? (count - done) : batch_max);
+    rc = sample_device(ctx, he_number, first_index + done, n, nullptr);
+    if (rc == HEROAM_OK) rc = heroam_gpu_run(ctx);
+    if (rc != HEROAM_OK) break;
+    Consts c;
+    make_consts(ctx->conf, he_number, &c);
+    DevView v = make_view(ctx, c);
+    k_stats<<<((unsigned)n + 127u) / 128u, 128, 0, ctx->main>>>(v, d_stats);
+    if (cudaGetLastError() != cudaSuccess) { rc = fail(HEROAM_E_CUDA, "k_stats launch failed"); break; }
+    total.trajectories += ctx->info.trajectories;
+    total.particles += ctx->info.particles;
+    total.particle_steps += ctx->info.particle_steps;
+    total.pair_steps += ctx->info.pair_steps;
+    total.inrange_steps += ctx->info.inrange_steps;
+    total.passes += ctx->info.passes;
+    total.kernel_launches += ctx->info.kernel_launches + 1;  // sampling (2) + passes + k_stats
+    total.integrate_ms += ctx->info.integrate_ms;
+  }
+  if (rc == HEROAM_OK) {
+    cudaEventRecord(e1, ctx->main);
+    DevStats *h = (DevStats *)malloc(sizeof(DevStats));
+    if (cudaMemcpyAsync(h, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->main) != cudaSuccess) {
+      rc = fail(HEROAM_E_CUDA, "statistics readback failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      total.device_ms = ms;
+      total.d2h_bytes = sizeof(DevStats);
+      memcpy(out->hist_n, h->hist_n, sizeof out->hist_n);
+      memcpy(out->hist_traj_time, h->hist_traj_time, sizeof out->hist_traj_time);
+      memcpy(out->hist_meet_time, h->hist_meet_time, sizeof out->hist_meet_time);
+      memcpy(out->done, h->done, sizeof out->done);
+      out->unmet_particles = h->unmet_particles;
+      out->particles = h->particles;
+      out->trajectories = h->trajectories;
+      out->sum_traj_time = h->sum_traj_time;
+      out->info = total;
+      ctx->info = total;
+    }
+    free(h);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_stats);
+  return rc;
+}
