@@ -73,7 +73,8 @@ typedef struct heroam_options {
   unsigned long long max_steps; /* per-trajectory cap on loop iterations (0 = none)         */
   int wide_kernel;        /* 0 = warp-per-trajectory kernel for > 8 moving particles (default);
                              1 = the slow record-resident kernel (cross-check only)        */
-  int reserved[3];
+  unsigned int pool_slots; /* trajectories kept in flight by heroam_gpu_run_stats (0 = 2^20)        */
+  int reserved[2];
 } heroam_options;
 
 typedef struct heroam_traj_result {

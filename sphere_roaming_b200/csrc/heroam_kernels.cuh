@@ -170,12 +170,89 @@ __device__ void finish_step(const DevView &v, TrajMeta &m, Counters &work) {
 }
 
 // ---------------------------------------------------------------------------------
-// k_resolve_and_bin: one thread per trajectory, once per pass.
+// Pieces of the per-pass bookkeeping, shared by k_resolve_and_bin (fixed batch) and
+// k_pool_resolve (streaming pool, heroam_sampler.cuh).
+// ---------------------------------------------------------------------------------
+constexpr uint32_t NOT_DONE = 0xffffffffu;
+
+// The loop condition `!success && time < max_time` (simulation.c:469) plus the defined
+// exits (deadlock, step cap, unsupported width).  Returns a HEROAM_DONE_* code or NOT_DONE.
+__device__ inline uint32_t evaluate_exit(const Consts &c, TrajMeta &m, uint32_t step_cap) {
+  uint32_t done = NOT_DONE;
+  if (m.steps == 0) {
+    if (!(0.0f < c.max_time)) {
+      done = HEROAM_DONE_MAXTIME;  // the reference's loop body never runs
+    } else if (step_cap == 0u) {
+      done = HEROAM_DONE_STEPCAP;
+    } else if (m.n_active == 0) {
+      // a step with nobody to move: forces are zeroed at import, no clock advances
+      m.steps = 1;
+      done = all_paired(m.no, m.n_flagged) ? HEROAM_DONE_SUCCESS : HEROAM_DONE_DEADLOCK;
+    }
+  } else if (all_paired(m.no, m.n_flagged)) {
+    done = HEROAM_DONE_SUCCESS;
+  } else if (!(m.time < c.max_time)) {
+    done = HEROAM_DONE_MAXTIME;
+  } else if (m.n_active == 0) {
+    done = HEROAM_DONE_DEADLOCK;
+  } else if (m.steps >= step_cap) {
+    done = HEROAM_DONE_STEPCAP;
+  }
+  if (done == NOT_DONE && m.n_active > (uint32_t)MAX_ACTIVE) done = HEROAM_DONE_UNSUPPORTED;
+  return done;
+}
+
+// List the active particles and fix the step at which the next segment ends; returns
+// the bin of the trajectory.
+__device__ inline int schedule_segment(const DevView &v, TrajMeta &m, uint32_t segment, uint32_t step_cap) {
+  uint32_t s = 0;
+  for (uint32_t j = 0; j < m.no; ++j)
+    if (!v.particles[m.first + j].success) v.act[m.first + s++] = j;
+  uint32_t stop = m.steps + segment;
+  if (stop < m.steps) stop = 0xffffffffu;
+  // the criterion already holds before the first step: the reference still runs exactly
+  // one iteration (do-while shape of simulation.c:466-469, Q2)
+  if (m.steps == 0 && all_paired(m.no, m.n_flagged)) stop = 1;
+  if (stop > v.c.max_steps) stop = v.c.max_steps;
+  if (stop > step_cap) stop = step_cap;
+  m.step_stop = stop;
+  return bin_of(m.n_active);
+}
+
+// Warp-aggregated append of trajectory t to bin `bin` (-1 = none): one atomic per
+// (warp, bin).  Must be called by all 32 lanes.
+__device__ inline void append_to_bin(int bin, uint32_t t, uint32_t stride, uint32_t *__restrict__ bin_count,
+                                     uint32_t *__restrict__ bin_list) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (bin >= 0) {
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(bin_count + bin, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    bin_list[(size_t)bin * stride + base + rank] = t;
+  }
+}
+
+__device__ inline void flush_work(const DevView &v, const Counters &work) {
+  const unsigned long long ps = warp_sum_u64(work.particle_steps);
+  const unsigned long long pr = warp_sum_u64(work.pair_steps);
+  const unsigned long long ir = warp_sum_u64(work.inrange_steps);
+  const unsigned long long un = warp_sum_u64(work.unsupported);
+  if ((threadIdx.x & 31u) == 0 && (ps | pr | ir | un)) {
+    atomicAdd(&v.counters->particle_steps, ps);
+    atomicAdd(&v.counters->pair_steps, pr);
+    atomicAdd(&v.counters->inrange_steps, ir);
+    if (un) atomicAdd(&v.counters->unsupported, un);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_resolve_and_bin: one thread per trajectory, once per pass (fixed batch).
 //   1. finish a pending meeting step;
-//   2. evaluate the loop condition `!success && time < max_time` (simulation.c:469)
-//      plus the defined exits (deadlock, step cap);
-//   3. list the active particles and append the trajectory to the bin of its
-//      active count with the step at which the next segment ends.
+//   2. evaluate the exit conditions;
+//   3. schedule the next segment and append the trajectory to the bin of its active count.
 // ---------------------------------------------------------------------------------
 template <class P>
 __global__ void k_resolve_and_bin(DevView v, uint32_t segment, uint32_t step_cap,
@@ -186,70 +263,19 @@ __global__ void k_resolve_and_bin(DevView v, uint32_t segment, uint32_t step_cap
   if (t < v.n_traj) {
     TrajMeta m = v.meta[t];
     if (m.status < ST_DONE) {
-      const Consts &c = v.c;
       if (m.status == ST_MIDSTEP) finish_step<P>(v, m, work);
-      uint32_t done = 0xffffffffu;
-      if (m.steps == 0) {
-        if (!(0.0f < c.max_time)) {
-          done = HEROAM_DONE_MAXTIME;  // the reference's loop body never runs
-        } else if (step_cap == 0u) {
-          done = HEROAM_DONE_STEPCAP;
-        } else if (m.n_active == 0) {
-          // a step with nobody to move: forces are zeroed (k_prepare), no clock advances
-          m.steps = 1;
-          done = all_paired(m.no, m.n_flagged) ? HEROAM_DONE_SUCCESS : HEROAM_DONE_DEADLOCK;
-        }
-      } else if (all_paired(m.no, m.n_flagged)) {
-        done = HEROAM_DONE_SUCCESS;
-      } else if (!(m.time < c.max_time)) {
-        done = HEROAM_DONE_MAXTIME;
-      } else if (m.n_active == 0) {
-        done = HEROAM_DONE_DEADLOCK;
-      } else if (m.steps >= step_cap) {
-        done = HEROAM_DONE_STEPCAP;
-      }
-      if (done == 0xffffffffu && m.n_active > (uint32_t)MAX_ACTIVE) {
-        done = HEROAM_DONE_UNSUPPORTED;
-        atomicAdd(&v.counters->unsupported, 1ull);
-      }
-      if (done != 0xffffffffu) {
+      const uint32_t done = evaluate_exit(v.c, m, step_cap);
+      if (done != NOT_DONE) {
         m.status = ST_DONE + done;
+        if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported = 1;
       } else {
-        uint32_t s = 0;
-        for (uint32_t j = 0; j < m.no; ++j)
-          if (!v.particles[m.first + j].success) v.act[m.first + s++] = j;
-        uint32_t stop = m.steps + segment;
-        if (stop < m.steps) stop = 0xffffffffu;
-        // the criterion already holds before the first step: the reference still runs
-        // exactly one iteration (do-while shape of :466-469, Q2)
-        if (m.steps == 0 && all_paired(m.no, m.n_flagged)) stop = 1;
-        if (stop > c.max_steps) stop = c.max_steps;
-        if (stop > step_cap) stop = step_cap;
-        m.step_stop = stop;
-        bin = bin_of(m.n_active);
+        bin = schedule_segment(v, m, segment, step_cap);
       }
       v.meta[t] = m;
     }
   }
-  // warp-aggregated append: one atomic per (warp, bin)
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned peers = __match_any_sync(0xffffffffu, bin);
-  if (bin >= 0) {
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(bin_count + bin, (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    bin_list[(size_t)bin * v.n_traj + base + rank] = t;
-  }
-  const unsigned long long ps = warp_sum_u64(work.particle_steps);
-  const unsigned long long pr = warp_sum_u64(work.pair_steps);
-  const unsigned long long ir = warp_sum_u64(work.inrange_steps);
-  if (lane == 0 && (ps | pr | ir)) {
-    atomicAdd(&v.counters->particle_steps, ps);
-    atomicAdd(&v.counters->pair_steps, pr);
-    atomicAdd(&v.counters->inrange_steps, ir);
-  }
+  append_to_bin(bin, t, v.n_traj, bin_count, bin_list);
+  flush_work(v, work);
 }
 
 // ---------------------------------------------------------------------------------

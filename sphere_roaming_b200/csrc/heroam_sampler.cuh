@@ -174,17 +174,10 @@ __device__ inline void initial_forces(const Consts &c, const float *__restrict__
   }
 }
 
-// stage 2: the particles of every trajectory (serial within a trajectory: one stream)
-__global__ void k_sample_particles(SampleParams sp, Consts c, const float *__restrict__ table, uint32_t n_traj,
-                                   const uint32_t *__restrict__ counts, const uint32_t *__restrict__ first,
-                                   const uint32_t *__restrict__ consumed, heroam_particle *__restrict__ particles) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_traj) return;
-  Philox g;
-  g.begin(sp.seed, sp.he_number, sp.first_index + t);
-  g.skip_to(consumed[t]);
-  const uint32_t n = counts[t];
-  heroam_particle *p = particles + first[t];
+// The n particles of one trajectory from its stream (positioned after the count draws),
+// then the initial calculate_force (simulation.c:311-334).
+__device__ inline void sample_trajectory(Philox &g, const SampleParams &sp, const Consts &c,
+                                         const float *__restrict__ table, heroam_particle *p, uint32_t n) {
   const float radius_f = (float)sp.radius_init;
   for (uint32_t j = 0; j < n; ++j) {
     heroam_particle out;
@@ -219,6 +212,18 @@ __global__ void k_sample_particles(SampleParams sp, Consts c, const float *__res
   initial_forces(c, table, p, n);
 }
 
+// stage 2: the particles of every trajectory (serial within a trajectory: one stream)
+__global__ void k_sample_particles(SampleParams sp, Consts c, const float *__restrict__ table, uint32_t n_traj,
+                                   const uint32_t *__restrict__ counts, const uint32_t *__restrict__ first,
+                                   const uint32_t *__restrict__ consumed, heroam_particle *__restrict__ particles) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_traj) return;
+  Philox g;
+  g.begin(sp.seed, sp.he_number, sp.first_index + t);
+  g.skip_to(consumed[t]);
+  sample_trajectory(g, sp, c, table, particles + first[t], counts[t]);
+}
+
 // ---------------------------------------------------------------------------------
 // statistics of a finished batch
 // ---------------------------------------------------------------------------------
@@ -238,10 +243,7 @@ __device__ __forceinline__ int time_bin(float t, float max_time) {
   return b < 0 ? 0 : (b >= HEROAM_HIST_T ? HEROAM_HIST_T - 1 : b);
 }
 
-__global__ void k_stats(DevView v, DevStats *__restrict__ st) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= v.n_traj) return;
-  const TrajMeta m = v.meta[t];
+__device__ inline void accumulate_stats(const DevView &v, const TrajMeta &m, DevStats *__restrict__ st) {
   atomicAdd(&st->hist_n[m.no < HEROAM_HIST_N ? m.no : HEROAM_HIST_N - 1], 1ull);
   atomicAdd(&st->hist_traj_time[time_bin(m.time, v.c.max_time)], 1ull);
   const uint32_t code = m.status >= ST_DONE ? m.status - ST_DONE : 7u;
@@ -256,6 +258,89 @@ __global__ void k_stats(DevView v, DevStats *__restrict__ st) {
   if (unmet) atomicAdd(&st->unmet_particles, unmet);
   atomicAdd(&st->particles, (unsigned long long)m.no);
   atomicAdd(&st->trajectories, 1ull);
+}
+
+__global__ void k_stats(DevView v, DevStats *__restrict__ st) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= v.n_traj) return;
+  accumulate_stats(v, v.meta[t], st);
+}
+
+// ---------------------------------------------------------------------------------
+// Streaming pool (retire and refill).  The device holds `n_traj` SLOTS of `cap` records
+// each.  Once per pass every slot is visited by one thread of k_pool_resolve:
+//   * a live trajectory gets its pending meeting step finished and its exit evaluated;
+//   * a finished one is folded into the histograms and its slot is freed;
+//   * a free slot claims the next trajectory index from a global cursor, samples that
+//     trajectory in place (Philox: count, particles, initial forces) and goes live;
+//   * live slots are binned by active count for the integrate kernels.
+// The heavy tail of trajectory lengths (1 .. 1e7 steps) therefore costs one drain at the
+// end of a run instead of one per batch.
+// ---------------------------------------------------------------------------------
+constexpr uint32_t ST_FREE = 0xfffffff0u;
+
+struct PoolParams {
+  SampleParams sp;
+  unsigned long long *cursor;   // next trajectory index (relative to sp.first_index)
+  unsigned long long count;     // trajectories in the run
+  uint32_t cap;                 // records per slot
+  DevStats *stats;
+};
+
+__global__ void k_pool_init(DevView v, uint32_t cap) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= v.n_traj) return;
+  TrajMeta m;
+  m.first = t * cap;
+  m.no = 0; m.steps = 0; m.time = 0.0f; m.n_flagged = 0; m.n_active = 0; m.step_stop = 0;
+  m.status = ST_FREE;
+  v.meta[t] = m;
+}
+
+template <class P>
+__global__ void k_pool_resolve(DevView v, PoolParams pool, uint32_t segment, uint32_t step_cap,
+                               uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  Counters work = {0, 0, 0, 0};
+  int bin = -1;
+  if (t < v.n_traj) {
+    TrajMeta m = v.meta[t];
+    if (m.status == ST_MIDSTEP) finish_step<P>(v, m, work);
+    // a freshly spawned trajectory can be over at once (nobody moving), hence the loop
+    for (;;) {
+      if (m.status < ST_DONE) {
+        const uint32_t done = evaluate_exit(v.c, m, step_cap);
+        if (done == NOT_DONE) break;
+        m.status = ST_DONE + done;
+        if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported += 1;
+      }
+      if (m.status != ST_FREE) {
+        accumulate_stats(v, m, pool.stats);
+        m.status = ST_FREE;
+      }
+      const unsigned long long idx = atomicAdd(pool.cursor, 1ull);
+      if (idx >= pool.count) break;
+      Philox g;
+      g.begin(pool.sp.seed, pool.sp.he_number, pool.sp.first_index + idx);
+      const uint32_t n = sample_count(g, pool.sp.limit);
+      m.no = n; m.steps = 0; m.time = 0.0f; m.n_flagged = 0; m.step_stop = 0;
+      if (n > pool.cap) {  // does not fit a slot: counted, not integrated
+        m.no = 0; m.n_active = 0;
+        m.status = ST_DONE + HEROAM_DONE_UNSUPPORTED;
+        work.unsupported += 1;
+        continue;
+      }
+      heroam_particle *p = v.particles + m.first;
+      sample_trajectory(g, pool.sp, v.c, v.table, p, n);
+      for (uint32_t j = 0; j < n; ++j) m.n_flagged += p[j].success ? 1u : 0u;
+      m.n_active = n - m.n_flagged;
+      m.status = ST_LIVE;
+    }
+    if (m.status < ST_DONE) bin = schedule_segment(v, m, segment, step_cap);
+    v.meta[t] = m;
+  }
+  append_to_bin(bin, t, v.n_traj, bin_count, bin_list);
+  flush_work(v, work);
 }
 
 }  // namespace heroam
@@ -362,67 +447,136 @@ extern "C" int heroam_gpu_sample_batch(heroam_ctx *ctx, unsigned long long he_nu
   return HEROAM_OK;
 }
 
+// slot capacity of the streaming pool: room for lambda + 8 sigma (+8), at most MAX_ACTIVE
+static uint32_t pool_slot_capacity(double lambda) {
+  const double want = lambda + 8.0 * sqrt(lambda) + 8.0;
+  uint32_t cap = 8;
+  while (cap < want && cap < (uint32_t)MAX_ACTIVE) cap *= 2;
+  return cap;
+}
+
+template <class P>
+static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, uint32_t slots) {
+  DevView v = make_view(ctx, c);
+  const unsigned tgrid = (slots + 127) / 128;
+  const uint32_t step_cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu
+                                                                                         : (uint32_t)ctx->opt.max_steps;
+  double integrate_ms = 0.0;
+  bool pending_timing = false;
+  k_pool_init<<<tgrid, 128, 0, ctx->main>>>(v, pool.cap);
+  CU(cudaGetLastError());
+  ctx->info.kernel_launches++;
+  for (;;) {
+    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
+    k_pool_resolve<P><<<tgrid, 128, 0, ctx->main>>>(v, pool, ctx->opt.segment_steps, step_cap, ctx->d_bin_count,
+                                                     ctx->d_bin_list);
+    CU(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaStreamSynchronize(ctx->main));
+    if (pending_timing) {
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, ctx->ev_i0, ctx->ev_i1));
+      integrate_ms += ms;
+      pending_timing = false;
+    }
+    uint64_t live = 0;
+    for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
+    if (live == 0) break;  // every slot is free and the index space is used up
+    ctx->info.passes++;
+    CU(cudaEventRecord(ctx->ev_i0, ctx->main));
+    for (int b = 1; b < N_BINS; ++b) {
+      const uint32_t cnt = ctx->h_bin_count[b];
+      if (!cnt) continue;
+      CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
+      int rc = launch_bin<P>(ctx, v, b, cnt);
+      if (rc) return rc;
+      ctx->info.kernel_launches++;
+      CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
+      CU(cudaStreamWaitEvent(ctx->main, ctx->bin_done[b], 0));
+    }
+    CU(cudaEventRecord(ctx->ev_i1, ctx->main));
+    pending_timing = true;
+  }
+  ctx->info.integrate_ms = integrate_ms;
+  return HEROAM_OK;
+}
+
 extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index,
                                     unsigned long long count, heroam_stats *out) {
   if (!ctx || !out) return fail(HEROAM_E_ARG, "heroam_gpu_run_stats: null argument");
   CU(cudaSetDevice(ctx->device));
   memset(out, 0, sizeof *out);
+  memset(&ctx->info, 0, sizeof ctx->info);
+  ctx->uploaded = false;
+  if (count == 0) return HEROAM_OK;
+  Consts c;
+  int rc = make_consts(ctx->conf, he_number, &c);
+  if (rc) return rc;
+  const double lambda = host_lambda(ctx->conf, he_number);
+  if (!(lambda > 0.0) || lambda > 700.0)
+    return fail(HEROAM_E_ARG, "mean excitation number %g outside (0, 700]: Knuth's product of uniforms "
+                "(simulation.c:257-275) is undefined there", lambda);
+  const uint32_t cap = pool_slot_capacity(lambda);
+  const unsigned long long pool_max = ctx->opt.pool_slots > 0 ? (unsigned long long)ctx->opt.pool_slots : (1ull << 20);
+  const uint32_t slots = (uint32_t)(count < pool_max ? count : pool_max);
+  rc = reserve(ctx, slots, (size_t)slots * cap);
+  if (rc) return rc;
+  ctx->he_number = he_number;
+  ctx->n_traj = slots;
+  ctx->n_particles = (size_t)slots * cap;
   DevStats *d_stats = nullptr;
+  unsigned long long *d_cursor = nullptr;
   CU(cudaMalloc(&d_stats, sizeof(DevStats)));
-  CU(cudaMemset(d_stats, 0, sizeof(DevStats)));
-  const unsigned long long batch_max = 1ull << 20;
-  heroam_run_info total;
-  memset(&total, 0, sizeof total);
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
-  CU(cudaEventRecord(e0, ctx->main));
-  int rc = HEROAM_OK;
-  for (unsigned long long done = 0; done < count && rc == HEROAM_OK; done += batch_max) {
-    const int n = (int)((count - done) < batch_max ? (count - done) : batch_max);
-    rc = sample_device(ctx, he_number, first_index + done, n, nullptr);
-    if (rc == HEROAM_OK) rc = heroam_gpu_run(ctx);
-    if (rc != HEROAM_OK) break;
-    Consts c;
-    make_consts(ctx->conf, he_number, &c);
-    DevView v = make_view(ctx, c);
-    k_stats<<<((unsigned)n + 127u) / 128u, 128, 0, ctx->main>>>(v, d_stats);
-    if (cudaGetLastError() != cudaSuccess) { rc = fail(HEROAM_E_CUDA, "k_stats launch failed"); break; }
-    total.trajectories += ctx->info.trajectories;
-    total.particles += ctx->info.particles;
-    total.particle_steps += ctx->info.particle_steps;
-    total.pair_steps += ctx->info.pair_steps;
-    total.inrange_steps += ctx->info.inrange_steps;
-    total.passes += ctx->info.passes;
-    total.kernel_launches += ctx->info.kernel_launches + 1;  // sampling (2) + passes + k_stats
-    total.integrate_ms += ctx->info.integrate_ms;
+  CU(cudaMalloc(&d_cursor, sizeof(unsigned long long)));
+  PoolParams pool;
+  pool.sp.seed = (long long)ctx->conf.seed;
+  pool.sp.he_number = he_number;
+  pool.sp.first_index = first_index;
+  pool.sp.limit = exp(-1.0 * lambda);
+  pool.sp.radius_init = 2.22 * pow((double)he_number, 1.0 / 3.0);
+  pool.sp.sigma = ctx->conf.velocity;
+  pool.cursor = d_cursor;
+  pool.count = count;
+  pool.cap = cap;
+  pool.stats = d_stats;
+  CU(cudaEventRecord(ctx->ev_start, ctx->main));
+  CU(cudaMemsetAsync(d_stats, 0, sizeof(DevStats), ctx->main));
+  CU(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->main));
+  CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
+  rc = ctx->opt.mode == HEROAM_MODE_EXACT ? run_pool<Exact>(ctx, c, pool, slots) : run_pool<Fast>(ctx, c, pool, slots);
+  DevStats *h = (DevStats *)malloc(sizeof(DevStats));
+  if (rc == HEROAM_OK) {
+    if (cudaMemcpyAsync(h, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
+        cudaEventRecord(ctx->ev_stop, ctx->main) != cudaSuccess || cudaStreamSynchronize(ctx->main) != cudaSuccess)
+      rc = fail(HEROAM_E_CUDA, "statistics readback failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (rc == HEROAM_OK) {
-    cudaEventRecord(e1, ctx->main);
-    DevStats *h = (DevStats *)malloc(sizeof(DevStats));
-    if (cudaMemcpyAsync(h, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->main) != cudaSuccess) {
-      rc = fail(HEROAM_E_CUDA, "statistics readback failed: %s", cudaGetErrorString(cudaGetLastError()));
-    } else {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, e0, e1);
-      total.device_ms = ms;
-      total.d2h_bytes = sizeof(DevStats);
-      memcpy(out->hist_n, h->hist_n, sizeof out->hist_n);
-      memcpy(out->hist_traj_time, h->hist_traj_time, sizeof out->hist_traj_time);
-      memcpy(out->hist_meet_time, h->hist_meet_time, sizeof out->hist_meet_time);
-      memcpy(out->done, h->done, sizeof out->done);
-      out->unmet_particles = h->unmet_particles;
-      out->particles = h->particles;
-      out->trajectories = h->trajectories;
-      out->sum_traj_time = h->sum_traj_time;
-      out->info = total;
-      ctx->info = total;
-    }
-    free(h);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+    ctx->info.device_ms = ms;
+    ctx->info.d2h_bytes = sizeof(DevStats);
+    ctx->info.trajectories = h->trajectories;
+    ctx->info.particles = h->particles;
+    ctx->info.particle_steps = ctx->h_counters->particle_steps;
+    ctx->info.pair_steps = ctx->h_counters->pair_steps;
+    ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
+    memcpy(out->hist_n, h->hist_n, sizeof out->hist_n);
+    memcpy(out->hist_traj_time, h->hist_traj_time, sizeof out->hist_traj_time);
+    memcpy(out->hist_meet_time, h->hist_meet_time, sizeof out->hist_meet_time);
+    memcpy(out->done, h->done, sizeof out->done);
+    out->unmet_particles = h->unmet_particles;
+    out->particles = h->particles;
+    out->trajectories = h->trajectories;
+    out->sum_traj_time = h->sum_traj_time;
+    out->info = ctx->info;
+    if (ctx->h_counters->unsupported)
+      rc = fail(HEROAM_E_UNSUPPORTED, "%llu trajectories have more than %d particles", ctx->h_counters->unsupported,
+                MAX_ACTIVE);
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  free(h);
   cudaFree(d_stats);
+  cudaFree(d_cursor);
   return rc;
 }

@@ -59,7 +59,8 @@ class Options(C.Structure):
         ("segment_steps", C.c_uint),
         ("max_steps", C.c_ulonglong),
         ("wide_kernel", C.c_int),
-        ("reserved", C.c_int * 3),
+        ("pool_slots", C.c_uint),
+        ("reserved", C.c_int * 2),
     ]
 
 
@@ -156,7 +157,7 @@ class Engine:
     """One GPU context (``heroam_gpu_create``): force table resident on the device."""
 
     def __init__(self, conf: Config, table: np.ndarray, device: int = 0, mode="exact", segment_steps: int = 0,
-                 max_steps: int = 0, wide_kernel: int = 0):
+                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0):
         self.lib = load_library()
         self.conf = conf
         table = np.ascontiguousarray(table, dtype=np.float32)
@@ -167,6 +168,7 @@ class Engine:
         opt.segment_steps = segment_steps
         opt.max_steps = max_steps
         opt.wide_kernel = wide_kernel
+        opt.pool_slots = pool_slots
         h = C.c_void_p()
         self._check(self.lib.heroam_gpu_create(C.byref(conf), table.ctypes.data_as(C.POINTER(C.c_float)), device,
                                                C.byref(opt), C.byref(h)))

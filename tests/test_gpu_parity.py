@@ -181,6 +181,7 @@ def test_edge_cases(need_gpu, port, table):
         p = np.zeros(8, dtype=PARTICLE_DTYPE)
         p["orientation"][:, 0] = 1.0
         p["position"] = [(0, 0, R), (0, 0, R), (1, 0, R), (0, 0, R), (0.5, 0, R), (0, 0.5, R), (0, 0, R), (0, 0, -R)]
+        p["orientation"][7] = (0, 1, 0, 0)  # half turn about x: this particle really sits at the south pole
         p["ang_velocity"][0] = (1e-5, 0, 0)
         p["success"][1:3] = 1
         p["force"][1] = (5, 5, 5)
@@ -222,3 +223,54 @@ def test_step_cap_and_resume_free_determinism(need_gpu, port, table):
     assert_records_equal(got, want, "step cap")
     assert got.tobytes() == again.tobytes()
     assert np.array_equal(res["status"], wres["status"]) and (res["status"] == 4).any()
+
+@pytest.mark.parametrize("pool_slots", [0, 700])
+def test_run_stats_streaming_pool_equals_batch_path(need_gpu, port, table, pool_slots):
+    """heroam_gpu_run_stats (streaming pool with retire-and-refill, sampling fused in) must
+    give exactly the statistics of sample + simulate on the same index block -- in exact
+    mode bit for bit against the CPU oracle, whatever the pool size."""
+    from sphere_roaming_b200.sharding import stats_from_records
+
+    n, max_time, first = 5000, 3.0e4, 777
+    conf = make_config(number=n, max_time=max_time)
+    counts, init = port.sample(conf, HE, table, n, source="philox", first_index=first)
+    final, res, ctr = port.simulate(conf, HE, table, counts, init, want_counters=True)
+    want = stats_from_records(counts, final, res, max_time)
+    with engine.Engine(conf, table, mode="exact", pool_slots=pool_slots, segment_steps=1000) as eng:
+        got = eng.run_stats(HE, n, first_index=first)
+    for key in ("hist_n", "hist_traj_time", "hist_meet_time", "done"):
+        assert np.array_equal(got[key], want[key]), key
+    assert got["trajectories"] == n and got["particles"] == int(counts.sum())
+    assert got["unmet_particles"] == want["unmet_particles"]
+    assert abs(got["sum_traj_time"] - want["sum_traj_time"]) < 1e-9 * want["sum_traj_time"]
+    assert got["info"]["particle_steps"] == ctr["particle_steps"]
+    assert got["info"]["pair_steps"] == ctr["pair_steps"] and got["info"]["inrange_steps"] == ctr["inrange_steps"]
+
+
+def test_full_size_properties(need_gpu, port, table):
+    """Size-independent properties on a large batch (a slice of config C2/C5: 2^18
+    trajectories, fast mode): every particle stays on the sphere, clocks never exceed the
+    horizon, flags come in meeting groups, sharding does not change the histograms."""
+    n, max_time = 1 << 18, 2.0e4
+    conf = make_config(number=n, max_time=max_time)
+    with engine.Engine(conf, table, mode="fast") as eng:
+        counts, init = eng.sample(HE, n)
+        final, res = eng.simulate(HE, counts, init)
+        whole = eng.run_stats(HE, n)
+        a = eng.run_stats(HE, n // 2)
+        b = eng.run_stats(HE, n - n // 2, first_index=n // 2)
+    R = port.radius_sim(HE)
+    assert np.allclose(np.linalg.norm(final["position"].astype(np.float64), axis=1), R, rtol=3e-6)
+    assert final["time"].max() <= max_time and res["time"].max() <= max_time
+    off = offsets_of(counts)
+    flagged = np.add.reduceat(final["success"], off[:-1])
+    assert np.array_equal(flagged, res["n_flagged"])
+    ok = res["status"] == 0
+    assert np.all(np.where(counts[ok] % 2 == 0, flagged[ok] == counts[ok], flagged[ok] == counts[ok] - 1))
+    assert np.all(final["time"][final["success"] == 0] >= 0)
+    # frozen particles carry zero force (Q8)
+    assert np.all(final["force"][final["success"] != 0] == 0)
+    for key in ("hist_n", "hist_traj_time", "hist_meet_time", "done"):
+        assert np.array_equal(whole[key], a[key] + b[key]), key
+    assert whole["trajectories"] == n
+    assert np.array_equal(whole["hist_n"][:64], np.bincount(counts, minlength=64)[:64])
