@@ -149,6 +149,33 @@ def sampler_streams(ref: RefOracle) -> dict:
                 speed_seed=np.int64(54321), speeds=speeds, quat_seed=np.int64(777), quats=quats)
 
 
+def particlefile_golden(ref: RefOracle, table: np.ndarray) -> None:
+    """particlefile text written by the reference's own save_particles (simulation.c:415-436)
+    under the header of main.c:65-69, for the first 6 golden trajectories."""
+    from sphere_roaming_b200.types import ParticlesC, offsets_of
+
+    g = np.load(os.path.join(HERE, "trajectories.npz"))
+    counts, final = g["counts"][:6], g["final"]
+    off = offsets_of(g["counts"])
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    libc.fputs.argtypes = [C.c_char_p, C.c_void_p]
+    ref.lib.save_particles.argtypes = [C.c_void_p, C.POINTER(ParticlesC)]
+    ref.lib.save_particles.restype = None
+    path = os.path.join(HERE, "particlefile_after_golden.tsv")
+    f = libc.fopen(path.encode(), b"w")
+    libc.fputs(b"Index\tNumber\tSuccess\tTime\tX\tY\tZ\tVX\tVY\tVZ\tFX\tFY\tFZ\n", f)
+    keep = []
+    for i in range(6):
+        rec = np.ascontiguousarray(final[off[i]:off[i + 1]])
+        keep.append(rec)
+        ps = ParticlesC(int(counts[i]), i, rec.ctypes.data)
+        ref.lib.save_particles(f, C.byref(ps))
+    libc.fclose(f)
+
+
 def main() -> None:
     ref = RefOracle("strict")
     assert ref.sizes() == (84, 16, 152)
@@ -161,8 +188,9 @@ def main() -> None:
     np.savez_compressed(os.path.join(HERE, "layout.npz"), sizes=np.array(ref.sizes()),
                         particle_offsets=np.array(ref.particle_offsets()), config_offsets=np.array(ref.config_offsets()),
                         table_head=table[:8], table_tail=table[-8:], table_sum=np.float64(table.astype(np.float64).sum()))
+    particlefile_golden(ref, table)
     for f in sorted(os.listdir(HERE)):
-        if f.endswith(".npz"):
+        if f.endswith((".npz", ".tsv")):
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
