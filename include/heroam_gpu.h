@@ -97,6 +97,9 @@ typedef struct heroam_run_info {
   double integrate_ms;    /* sum of CUDA-event times of the integrate kernels alone        */
   double h2d_ms, d2h_ms;  /* CUDA-event times of the copies (0 for resident runs)          */
   unsigned long long h2d_bytes, d2h_bytes;
+  unsigned long long pair_skipped;   /* pair-steps of free-flight segments: part of pair_steps, but
+                                        provably force-free and never evaluated               */
+  unsigned long long free_steps;     /* particle-steps taken in free flight (part of particle_steps) */
 } heroam_run_info;
 
 #define HEROAM_HIST_N 256

@@ -1,0 +1,15 @@
+"""Per-pass trace of a pooled run (HEROAM_TRACE=1): bin populations and integrate time."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sphere_roaming_b200 import engine
+from sphere_roaming_b200.forcetable import synthetic_table
+from sphere_roaming_b200.types import make_config
+N = int(os.environ.get("N", 1 << 20)); MT = float(os.environ.get("MT", 1e7))
+conf = make_config(number=N, max_time=MT)
+with engine.Engine(conf, synthetic_table(), mode=os.environ.get("MODE", "fast"), segment_steps=int(os.environ.get("SEG", 0)),
+                   pool_slots=int(os.environ.get("POOL", 0))) as eng:
+    eng.run_stats(10000, 4096)
+    st = eng.run_stats(10000, N)
+    i = st["info"]
+    print("RESULT particle-steps/s %.4g  device_ms %.1f integrate_ms %.1f passes %d launches %d" % (
+        i["particle_steps"] / i["device_ms"] * 1e3, i["device_ms"], i["integrate_ms"], i["passes"], i["kernel_launches"]))

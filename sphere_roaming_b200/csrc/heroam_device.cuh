@@ -26,6 +26,8 @@ enum : uint32_t {
   ST_LIVE = 0,     // clean state at a step boundary
   ST_MIDSTEP = 1,  // a pair came within icd_dist during the step: drift done, greedy
                    // meeting sweep + force + second kick still to do (resolve kernel)
+  ST_FLYING = 2,   // scheduled into the free-flight kernel for [steps, step_stop): the next
+                   // resolve pass commits steps/time (the kernel never writes TrajMeta)
   ST_DONE = 16     // ST_DONE + HEROAM_DONE_* once finished
 };
 
@@ -53,6 +55,7 @@ struct Consts {
   int grid_len;      // :219 (clamped to INT_MAX on the host)
   uint32_t max_steps;   // steps until the float clock reaches max_time (host-iterated)
   // fast-mode folded constants
+  float far2;        // squared distance beyond which a pair can neither feel force nor meet (with margin)
   float kick;        // acc_scale * half_dt
   float radius2;     // 2 * radius
 };
@@ -62,6 +65,8 @@ struct Counters {     // roofline work counters
   unsigned long long pair_steps;
   unsigned long long inrange_steps;
   unsigned long long unsupported;   // trajectories refused for having too many moving particles
+  unsigned long long pair_skipped;  // pair-steps of free-flight segments: counted in pair_steps, never evaluated
+  unsigned long long free_steps;    // particle-steps taken in free flight (orientation update only)
 };
 
 struct DevView {       // everything a kernel needs, passed by value
@@ -149,10 +154,13 @@ __device__ __forceinline__ void half_kick(const Consts &c, const float r[3], con
   }
 }
 
-// update_orientation (simulation.c:394-413): q += (dt/2) (0,w) q ; q /= |q| ;
-// r = R * q (0,0,1) q^-1  (vector.c:94-110, :191-205, :182-188).
+// update_orientation (simulation.c:394-413) in two halves:
+//   advance_orientation : q += (dt/2) (0,w) q ; q /= |q|
+//   pole_position       : r = R * q (0,0,1) q^-1   (vector.c:94-110, :191-205, :182-188)
+// The position depends on nothing but the new q, so a particle that is guaranteed to feel
+// no force (free flight) only needs the first half per step and the second once at the end.
 template <class P>
-__device__ __forceinline__ void drift(const Consts &c, const float w[3], float q[4], float r[3]) {
+__device__ __forceinline__ void advance_orientation(const Consts &c, const float w[3], float q[4]) {
   const float qa = q[0], qx = q[1], qy = q[2], qz = q[3];
   const float ox = w[0], oy = w[1], oz = w[2];
   if (P::exact) {
@@ -166,8 +174,25 @@ __device__ __forceinline__ void drift(const Consts &c, const float w[3], float q
     float ny = P::add(qy, P::mul(ty, c.half_dt));
     float nz = P::add(qz, P::mul(tz, c.half_dt));
     const float inv = __frcp_rn(__fsqrt_rn(P::dot4(na, nx, ny, nz)));
-    na = P::mul(na, inv); nx = P::mul(nx, inv); ny = P::mul(ny, inv); nz = P::mul(nz, inv);
-    q[0] = na; q[1] = nx; q[2] = ny; q[3] = nz;
+    q[0] = P::mul(na, inv); q[1] = P::mul(nx, inv); q[2] = P::mul(ny, inv); q[3] = P::mul(nz, inv);
+  } else {
+    const float ta = -fmaf(oz, qz, fmaf(oy, qy, ox * qx));
+    const float tx = fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
+    const float ty = fmaf(oz, qx, fmaf(-ox, qz, oy * qa));
+    const float tz = fmaf(oz, qa, fmaf(-oy, qx, ox * qy));
+    const float na = fmaf(ta, c.half_dt, qa);
+    const float nx = fmaf(tx, c.half_dt, qx);
+    const float ny = fmaf(ty, c.half_dt, qy);
+    const float nz = fmaf(tz, c.half_dt, qz);
+    const float inv = rsqrtf(P::dot4(na, nx, ny, nz));
+    q[0] = na * inv; q[1] = nx * inv; q[2] = ny * inv; q[3] = nz * inv;
+  }
+}
+
+template <class P>
+__device__ __forceinline__ void pole_position(const Consts &c, const float q[4], float r[3]) {
+  const float na = q[0], nx = q[1], ny = q[2], nz = q[3];
+  if (P::exact) {
     // q^-1 = conj(q)/|q|^2 ; t = q (x) (0,0,0,1) = (-qz, qy, -qx, qa) ; res = t (x) q^-1
     const float n2 = P::dot4(na, nx, ny, nz);
     const float ia = __fdiv_rn(na, n2);
@@ -182,22 +207,17 @@ __device__ __forceinline__ void drift(const Consts &c, const float w[3], float q
     r[1] = P::mul(ry, c.radius);
     r[2] = P::mul(rz, c.radius);
   } else {
-    const float ta = -fmaf(oz, qz, fmaf(oy, qy, ox * qx));
-    const float tx = fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
-    const float ty = fmaf(oz, qx, fmaf(-ox, qz, oy * qa));
-    const float tz = fmaf(oz, qa, fmaf(-oy, qx, ox * qy));
-    float na = fmaf(ta, c.half_dt, qa);
-    float nx = fmaf(tx, c.half_dt, qx);
-    float ny = fmaf(ty, c.half_dt, qy);
-    float nz = fmaf(tz, c.half_dt, qz);
-    const float inv = rsqrtf(P::dot4(na, nx, ny, nz));
-    na *= inv; nx *= inv; ny *= inv; nz *= inv;
-    q[0] = na; q[1] = nx; q[2] = ny; q[3] = nz;
     // unit q: q (0,0,1) q^-1 = (2(xz + ay), 2(yz - ax), a^2 - x^2 - y^2 + z^2)
     r[0] = c.radius2 * fmaf(nx, nz, na * ny);
     r[1] = c.radius2 * fmaf(ny, nz, -(na * nx));
     r[2] = c.radius * (fmaf(na, na, nz * nz) - fmaf(nx, nx, ny * ny));
   }
+}
+
+template <class P>
+__device__ __forceinline__ void drift(const Consts &c, const float w[3], float q[4], float r[3]) {
+  advance_orientation<P>(c, w, q);
+  pole_position<P>(c, q, r);
 }
 
 // One pair (simulation.c:192-197 and :216-229).  Returns d; adds the table force to

@@ -51,6 +51,8 @@ struct heroam_ctx {
   size_t cap_particles = 0;
   TrajMeta *d_meta = nullptr;
   uint32_t *d_act = nullptr, *d_first = nullptr, *d_counts = nullptr, *d_bin_list = nullptr;
+  uint2 *d_free_list = nullptr;  // (trajectory, active slot) per particle in free flight, N_FREE_TIERS lists
+  uint32_t free_stride = 0;      // entries per tier
   heroam_traj_result *d_results = nullptr;
   size_t cap_traj = 0;
   uint32_t *d_bin_count = nullptr;
@@ -111,6 +113,11 @@ static int make_consts(const heroam_config &conf, unsigned long long he_number, 
     return fail(HEROAM_E_CLOCK,
                 "dt=%g cannot advance a float clock up to max_time=%g: the reference's loop would never end",
                 (double)conf.dt, (double)conf.max_time);
+  {  // beyond this squared distance a pair is outside the table and outside icd_dist, with margin
+    const double table_end = (double)conf.force_grid_start + ((double)c.grid_len + 2.0) * (double)conf.force_grid * 1.000001;
+    const double reach2 = table_end > (double)c.icd2 ? table_end : (double)c.icd2;
+    c.far2 = (float)(reach2 * 1.0001 + 1.0e-3);
+  }
   c.kick = c.acc_scale * c.half_dt;
   c.radius2 = 2.0f * c.radius;
   *out = c;
@@ -174,6 +181,7 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
   cudaFree(ctx->d_particles);
   cudaFree(ctx->d_meta);
   cudaFree(ctx->d_act);
+  cudaFree(ctx->d_free_list);
   cudaFree(ctx->d_first);
   cudaFree(ctx->d_counts);
   cudaFree(ctx->d_bin_list);
@@ -214,6 +222,8 @@ static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
   }
   if (n_traj > ctx->cap_traj) {
     cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_free_list);
+    ctx->d_free_list = nullptr;
     cudaFree(ctx->d_first);
     cudaFree(ctx->d_counts);
     cudaFree(ctx->d_bin_list);
@@ -227,6 +237,9 @@ static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
     CU(cudaMalloc(&ctx->d_counts, n_traj * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_bin_list, (size_t)N_BINS * n_traj * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_results, n_traj * sizeof(heroam_traj_result)));
+    // only trajectories with <= FREE_MAX_A moving particles ever fly: FREE_MAX_A entries each suffice
+    ctx->free_stride = (uint32_t)(n_traj * FREE_MAX_A > 0xffffffffull ? 0xffffffffull : n_traj * FREE_MAX_A);
+    CU(cudaMalloc(&ctx->d_free_list, (size_t)N_FREE_TIERS * ctx->free_stride * sizeof(uint2)));
     ctx->cap_traj = n_traj;
   }
   return HEROAM_OK;
@@ -283,6 +296,11 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) 
   const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
+  if (bin >= BIN_FREE) {
+    k_free_flight<P><<<(cnt + 127) / 128, 128, 0, s>>>(v, ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride, cnt);
+    CU(cudaGetLastError());
+    return HEROAM_OK;
+  }
   switch (bin) {
     case 1: k_integrate_thread<1, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
     case 2: k_integrate_thread<2, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
@@ -314,6 +332,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
                                                                                     : (uint32_t)ctx->opt.max_steps;
   double integrate_ms = 0.0;
   bool pending_timing = false;
+  bool draining = false;
   CU(cudaEventRecord(ctx->ev_start, ctx->main));
   CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
   k_prepare<<<tgrid, 128, 0, ctx->main>>>(v, ctx->d_first, ctx->d_counts);
@@ -321,7 +340,10 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   ctx->info.kernel_launches++;
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
-    k_resolve_and_bin<P><<<tgrid, 128, 0, ctx->main>>>(v, ctx->opt.segment_steps, cap, ctx->d_bin_count, ctx->d_bin_list);
+    Segments sg = make_segments(ctx->opt.segment_steps);
+    sg.free_stride = ctx->free_stride;
+    sg.drain = draining ? 1u : 0u;
+    k_resolve_and_bin<P><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
@@ -335,6 +357,12 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     uint64_t live = 0;
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
     if (live == 0) break;
+    {
+      uint64_t trajectories = 0, flying = 0;
+      for (int b = 1; b < BIN_FREE; ++b) trajectories += ctx->h_bin_count[b];
+      for (int b = BIN_FREE; b < N_BINS; ++b) flying += ctx->h_bin_count[b];
+      draining = trajectories + flying / 2 < (uint64_t)ctx->sm_count * 256;
+    }
     ctx->info.passes++;
     CU(cudaEventRecord(ctx->ev_i0, ctx->main));
     for (int b = 1; b < N_BINS; ++b) {
@@ -364,6 +392,8 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   ctx->info.particle_steps = ctx->h_counters->particle_steps;
   ctx->info.pair_steps = ctx->h_counters->pair_steps;
   ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
+  ctx->info.pair_skipped = ctx->h_counters->pair_skipped;
+  ctx->info.free_steps = ctx->h_counters->free_steps;
   ctx->info.trajectories = n;
   ctx->info.particles = ctx->n_particles;
   if (ctx->h_counters->unsupported)

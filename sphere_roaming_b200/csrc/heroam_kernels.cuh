@@ -24,7 +24,12 @@ constexpr int THREAD_MAX_A = 8;   // bins 1..8: k_integrate_thread<A>, one threa
 constexpr int BIN_WARP1 = 9;      // 9..32 active: k_integrate_warp<1>, one warp per trajectory
 constexpr int BIN_WARP2 = 10;     // 33..64 active: k_integrate_warp<2> (two particles per lane)
 constexpr int BIN_WARP4 = 11;     // 65..128 active: k_integrate_warp<4>
-constexpr int N_BINS = 12;
+// every pair provably out of reach for a whole segment: k_free_flight, one thread per PARTICLE.
+// Three tiers of FIXED segment length (so that all lanes of a warp run the same trip count):
+constexpr int BIN_FREE = 12;      // BIN_FREE + 0: short, + 1: medium, + 2: long
+constexpr int N_FREE_TIERS = 3;
+constexpr int N_BINS = BIN_FREE + N_FREE_TIERS;
+constexpr int FREE_MAX_A = 8;     // the free-flight analysis is done for trajectories with <= 8 moving particles
 constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
 constexpr int INTEGRATE_TPB = 128;
 constexpr int WARP_KERNEL_WARPS = 4;  // warps (= trajectories) per block of k_integrate_warp
@@ -202,13 +207,83 @@ __device__ inline uint32_t evaluate_exit(const Consts &c, TrajMeta &m, uint32_t 
   return done;
 }
 
-// List the active particles and fix the step at which the next segment ends; returns
-// the bin of the trajectory.
-__device__ inline int schedule_segment(const DevView &v, TrajMeta &m, uint32_t segment, uint32_t step_cap) {
+// Steps a trajectory may advance per pass, by bin.  All bin kernels of a pass run concurrently
+// and the pass ends with the slowest, so bins whose step has a long dependency chain (many
+// particles per thread) get shorter segments and the cheap free-flight steps longer ones.
+struct Segments {
+  uint32_t of_bin[N_BINS];
+  uint32_t free_stride;   // entries reserved per free-flight tier in the free list
+  uint32_t drain;         // 1 while the run is draining (few live trajectories, latency bound):
+                          // the short free-flight tier would only slow per-pass progress
+};
+
+__host__ inline Segments make_segments(uint32_t base) {
+  Segments sg;
+  auto scaled = [base](uint32_t num, uint32_t den) { uint32_t v = (uint32_t)((unsigned long long)base * num / den); return v ? v : 1u; };
+  sg.of_bin[0] = base;
+  sg.of_bin[1] = sg.of_bin[2] = scaled(2, 1);
+  sg.of_bin[3] = sg.of_bin[4] = base;
+  sg.of_bin[5] = sg.of_bin[6] = scaled(1, 2);
+  sg.of_bin[7] = sg.of_bin[8] = scaled(1, 4);
+  sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 4);
+  sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
+  sg.of_bin[BIN_FREE + 1] = scaled(2, 1);
+  sg.of_bin[BIN_FREE + 2] = scaled(16, 1);
+  return sg;
+}
+
+// Free-flight horizon: the number of steps for which NO active pair of the trajectory can
+// come within reach of the force table or of icd_dist, whatever happens.  While that holds
+// every force is exactly zero, angular velocities are constant and the particles are
+// independent.  Bound: a particle with angular velocity w moves its position by at most
+// |w| R dt per step (chord <= arc; rotation angle per step is 2 atan(|w| dt / 2) <= |w| dt),
+// plus rounding of the re-projection (a few ulp of R).  A pair now D apart therefore stays
+// farther than D_far for at least (D - D_far) / (b_j + b_k) steps.  Evaluated in double with
+// 1 % slack on the speeds; forces must be exactly zero on entry (they are whenever the
+// state came out of a step in which every pair was out of range).
+__device__ inline uint32_t free_flight_horizon(const DevView &v, const TrajMeta &m) {
+  const uint32_t a = m.n_active;
+  if (a == 0 || a > (uint32_t)FREE_MAX_A) return 0;
+  const heroam_particle *base = v.particles + m.first;
+  const uint32_t *act = v.act + m.first;
+  double px[FREE_MAX_A], py[FREE_MAX_A], pz[FREE_MAX_A], reach[FREE_MAX_A];
+  const double R = (double)v.c.radius, dt = (double)v.c.dt;
+  for (uint32_t s = 0; s < a; ++s) {
+    const heroam_particle *p = base + act[s];
+    if (p->force[0] != 0.0f || p->force[1] != 0.0f || p->force[2] != 0.0f) return 0;
+    px[s] = p->position[0]; py[s] = p->position[1]; pz[s] = p->position[2];
+    const double wx = p->ang_velocity[0], wy = p->ang_velocity[1], wz = p->ang_velocity[2];
+    reach[s] = sqrt(wx * wx + wy * wy + wz * wz) * R * dt * 1.01 + 2.0e-6 * R;
+  }
+  if (a == 1) return 0xffffffffu;
+  const double d_far = sqrt((double)v.c.far2);
+  double horizon = 4.0e9;
+  for (uint32_t j = 0; j + 1 < a; ++j)
+    for (uint32_t k = j + 1; k < a; ++k) {
+      const double dx = px[j] - px[k], dy = py[j] - py[k], dz = pz[j] - pz[k];
+      const double gap = sqrt(dx * dx + dy * dy + dz * dz) - d_far;
+      if (!(gap > 0.0)) return 0;
+      const double h = gap / (reach[j] + reach[k]) - 2.0;
+      if (h < horizon) horizon = h;
+    }
+  return horizon < 1.0 ? 0u : (horizon > 4.0e9 ? 0xffffffffu : (uint32_t)horizon);
+}
+
+// List the active particles, choose the bin, and fix the step at which the segment ends.
+__device__ inline int schedule_segment(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap) {
   uint32_t s = 0;
   for (uint32_t j = 0; j < m.no; ++j)
     if (!v.particles[m.first + j].success) v.act[m.first + s++] = j;
-  uint32_t stop = m.steps + segment;
+  int bin = bin_of(m.n_active);
+  const uint32_t horizon = free_flight_horizon(v, m);
+  // A short guaranteed horizon (a pair hovering just outside the table) would make the pass
+  // advance this trajectory by a few steps only: the full kernel's fixed-length segment is the
+  // better deal below a quarter of it.
+  // The longest fixed-length tier the guaranteed horizon covers; a horizon shorter than the
+  // shortest tier (a pair hovering just outside the table) goes to the full kernel.
+  for (int tier = N_FREE_TIERS - 1; tier >= (sg.drain ? 1 : 0); --tier)
+    if (horizon >= sg.of_bin[BIN_FREE + tier]) { bin = BIN_FREE + tier; break; }
+  uint32_t stop = m.steps + sg.of_bin[bin];
   if (stop < m.steps) stop = 0xffffffffu;
   // the criterion already holds before the first step: the reference still runs exactly
   // one iteration (do-while shape of simulation.c:466-469, Q2)
@@ -216,22 +291,43 @@ __device__ inline int schedule_segment(const DevView &v, TrajMeta &m, uint32_t s
   if (stop > v.c.max_steps) stop = v.c.max_steps;
   if (stop > step_cap) stop = step_cap;
   m.step_stop = stop;
-  return bin_of(m.n_active);
+  if (bin >= BIN_FREE) m.status = ST_FLYING;
+  return bin;
+}
+
+// Commit a free-flight segment (the kernel leaves TrajMeta alone): the trajectory is now at
+// step_stop; its clock is the one the particles carry.
+__device__ inline void land_free_flight(const DevView &v, TrajMeta &m, Counters &work) {
+  const unsigned long long k = m.step_stop - m.steps;
+  m.steps = m.step_stop;
+  m.time = v.particles[m.first + v.act[m.first]].time;
+  m.status = ST_LIVE;
+  const unsigned long long a = m.n_active;
+  work.particle_steps += k * a;
+  work.pair_steps += k * (a * (a - 1) / 2);
+  work.pair_skipped += k * (a * (a - 1) / 2);
+  work.free_steps += k * a;
 }
 
 // Warp-aggregated append of trajectory t to bin `bin` (-1 = none): one atomic per
-// (warp, bin).  Must be called by all 32 lanes.
-__device__ inline void append_to_bin(int bin, uint32_t t, uint32_t stride, uint32_t *__restrict__ bin_count,
-                                     uint32_t *__restrict__ bin_list) {
+// (warp, bin).  Must be called by all 32 lanes.  The free-flight bin takes one entry per
+// moving PARTICLE: (trajectory, slot in its active list).
+__device__ inline void append_to_bin(int bin, uint32_t t, uint32_t n_active, uint32_t stride,
+                                     uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list,
+                                     uint2 *__restrict__ free_list, uint32_t free_stride) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned peers = __match_any_sync(0xffffffffu, bin);
-  if (bin >= 0) {
+  if (bin >= 0 && bin < BIN_FREE) {
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
     if ((int)lane == leader) base = atomicAdd(bin_count + bin, (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     bin_list[(size_t)bin * stride + base + rank] = t;
+  } else if (bin >= BIN_FREE) {
+    const uint32_t base = atomicAdd(bin_count + bin, n_active);
+    uint2 *list = free_list + (size_t)(bin - BIN_FREE) * free_stride;
+    for (uint32_t s = 0; s < n_active; ++s) list[base + s] = make_uint2(t, s);
   }
 }
 
@@ -240,11 +336,15 @@ __device__ inline void flush_work(const DevView &v, const Counters &work) {
   const unsigned long long pr = warp_sum_u64(work.pair_steps);
   const unsigned long long ir = warp_sum_u64(work.inrange_steps);
   const unsigned long long un = warp_sum_u64(work.unsupported);
+  const unsigned long long sk = warp_sum_u64(work.pair_skipped);
+  const unsigned long long fs = warp_sum_u64(work.free_steps);
   if ((threadIdx.x & 31u) == 0 && (ps | pr | ir | un)) {
     atomicAdd(&v.counters->particle_steps, ps);
     atomicAdd(&v.counters->pair_steps, pr);
     atomicAdd(&v.counters->inrange_steps, ir);
     if (un) atomicAdd(&v.counters->unsupported, un);
+    if (sk) atomicAdd(&v.counters->pair_skipped, sk);
+    if (fs) atomicAdd(&v.counters->free_steps, fs);
   }
 }
 
@@ -255,27 +355,63 @@ __device__ inline void flush_work(const DevView &v, const Counters &work) {
 //   3. schedule the next segment and append the trajectory to the bin of its active count.
 // ---------------------------------------------------------------------------------
 template <class P>
-__global__ void k_resolve_and_bin(DevView v, uint32_t segment, uint32_t step_cap,
-                                  uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list) {
+__global__ void k_resolve_and_bin(DevView v, Segments sg, uint32_t step_cap, uint32_t *__restrict__ bin_count,
+                                  uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  Counters work = {0, 0, 0, 0};
+  Counters work = {};
   int bin = -1;
+  uint32_t n_active = 0;
   if (t < v.n_traj) {
     TrajMeta m = v.meta[t];
     if (m.status < ST_DONE) {
       if (m.status == ST_MIDSTEP) finish_step<P>(v, m, work);
+      else if (m.status == ST_FLYING) land_free_flight(v, m, work);
       const uint32_t done = evaluate_exit(v.c, m, step_cap);
       if (done != NOT_DONE) {
         m.status = ST_DONE + done;
         if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported = 1;
       } else {
-        bin = schedule_segment(v, m, segment, step_cap);
+        bin = schedule_segment(v, m, sg, step_cap);
+        n_active = m.n_active;
       }
       v.meta[t] = m;
     }
   }
-  append_to_bin(bin, t, v.n_traj, bin_count, bin_list);
+  append_to_bin(bin, t, n_active, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
   flush_work(v, work);
+}
+
+// ---------------------------------------------------------------------------------
+// k_free_flight: one thread per moving PARTICLE of a trajectory whose pairs are all out of
+// reach for the whole segment.  Zero force: the half kicks add +-0, w stays what it is, and a
+// step is nothing but the orientation update; the position (only needed by the pair loop)
+// is rebuilt once at the end.  Per step this performs exactly the operations the full
+// kernels perform on that particle, so the records it leaves are bit-identical.
+// ---------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__restrict__ list, uint32_t count) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= count) return;
+  const Consts &c = v.c;
+  const uint2 e = list[item];
+  const TrajMeta m = v.meta[e.x];  // read only: the next resolve pass commits steps and time
+  heroam_particle *p = v.particles + m.first + v.act[m.first + e.y];
+  float q[4] = {p->orientation[0], p->orientation[1], p->orientation[2], p->orientation[3]};
+  float w[3];
+  ld3(p->ang_velocity, w);
+  float time = m.time;
+  for (uint32_t k = m.steps; k < m.step_stop; ++k) {
+    advance_orientation<P>(c, w, q);
+    time = __fadd_rn(time, c.dt);
+  }
+  float r[3], vel[3], v2;
+  pole_position<P>(c, q, r);
+  stored_velocity<P>(r, w, vel, v2);
+  p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
+  st3(p->position, r);
+  st3(p->velocity, vel);
+  p->velocity_sq = v2;
+  p->time = time;
 }
 
 // ---------------------------------------------------------------------------------

@@ -298,14 +298,17 @@ __global__ void k_pool_init(DevView v, uint32_t cap) {
 }
 
 template <class P>
-__global__ void k_pool_resolve(DevView v, PoolParams pool, uint32_t segment, uint32_t step_cap,
-                               uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list) {
+__global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t step_cap,
+                               uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list,
+                               uint2 *__restrict__ free_list) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  Counters work = {0, 0, 0, 0};
+  Counters work = {};
   int bin = -1;
+  uint32_t n_active = 0;
   if (t < v.n_traj) {
     TrajMeta m = v.meta[t];
     if (m.status == ST_MIDSTEP) finish_step<P>(v, m, work);
+    else if (m.status == ST_FLYING) land_free_flight(v, m, work);
     // a freshly spawned trajectory can be over at once (nobody moving), hence the loop
     for (;;) {
       if (m.status < ST_DONE) {
@@ -336,10 +339,13 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, uint32_t segment, uin
       m.n_active = n - m.n_flagged;
       m.status = ST_LIVE;
     }
-    if (m.status < ST_DONE) bin = schedule_segment(v, m, segment, step_cap);
+    if (m.status < ST_DONE) {
+      bin = schedule_segment(v, m, sg, step_cap);
+      n_active = m.n_active;
+    }
     v.meta[t] = m;
   }
-  append_to_bin(bin, t, v.n_traj, bin_count, bin_list);
+  append_to_bin(bin, t, n_active, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
   flush_work(v, work);
 }
 
@@ -463,13 +469,18 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
                                                                                          : (uint32_t)ctx->opt.max_steps;
   double integrate_ms = 0.0;
   bool pending_timing = false;
+  const bool trace = getenv("HEROAM_TRACE") != nullptr;  // per-pass bin populations and times on stderr
+  bool draining = false;  // set once fewer trajectories are live than fill the GPU: latency-bound regime
   k_pool_init<<<tgrid, 128, 0, ctx->main>>>(v, pool.cap);
   CU(cudaGetLastError());
   ctx->info.kernel_launches++;
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
-    k_pool_resolve<P><<<tgrid, 128, 0, ctx->main>>>(v, pool, ctx->opt.segment_steps, step_cap, ctx->d_bin_count,
-                                                     ctx->d_bin_list);
+    Segments sg = make_segments(ctx->opt.segment_steps);
+    sg.free_stride = ctx->free_stride;
+    sg.drain = draining ? 1u : 0u;
+    k_pool_resolve<P><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
+                                                     ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
@@ -479,11 +490,27 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
       CU(cudaEventElapsedTime(&ms, ctx->ev_i0, ctx->ev_i1));
       integrate_ms += ms;
       pending_timing = false;
+      if (trace) {
+        Counters now;
+        cudaMemcpy(&now, ctx->d_counters, sizeof now, cudaMemcpyDeviceToHost);
+        fprintf(stderr, " %.3f ms  psteps %llu free %llu\n", ms, now.particle_steps, now.free_steps);
+      }
     }
     uint64_t live = 0;
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
     if (live == 0) break;  // every slot is free and the index space is used up
+    {
+      uint64_t trajectories = 0;
+      for (int b = 1; b < BIN_FREE; ++b) trajectories += ctx->h_bin_count[b];
+      uint64_t flying = 0;
+      for (int b = BIN_FREE; b < N_BINS; ++b) flying += ctx->h_bin_count[b];
+      draining = trajectories + flying / 2 < (uint64_t)ctx->sm_count * 256;
+    }
     ctx->info.passes++;
+    if (trace) {
+      fprintf(stderr, "pass %llu live %llu bins", ctx->info.passes, (unsigned long long)live);
+      for (int b = 1; b < N_BINS; ++b) fprintf(stderr, " %u", ctx->h_bin_count[b]);
+    }
     CU(cudaEventRecord(ctx->ev_i0, ctx->main));
     for (int b = 1; b < N_BINS; ++b) {
       const uint32_t cnt = ctx->h_bin_count[b];
@@ -562,6 +589,8 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
     ctx->info.particle_steps = ctx->h_counters->particle_steps;
     ctx->info.pair_steps = ctx->h_counters->pair_steps;
     ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
+    ctx->info.pair_skipped = ctx->h_counters->pair_skipped;
+  ctx->info.free_steps = ctx->h_counters->free_steps;
     memcpy(out->hist_n, h->hist_n, sizeof out->hist_n);
     memcpy(out->hist_traj_time, h->hist_traj_time, sizeof out->hist_traj_time);
     memcpy(out->hist_meet_time, h->hist_meet_time, sizeof out->hist_meet_time);

@@ -79,6 +79,8 @@ class RunInfo(C.Structure):
         ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_ulonglong),
         ("d2h_bytes", C.c_ulonglong),
+        ("pair_skipped", C.c_ulonglong),
+        ("free_steps", C.c_ulonglong),
     ]
 
     def as_dict(self) -> dict:

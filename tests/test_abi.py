@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     # heroam_options: int, uint, ull, int, int[3]; heroam_traj_result: 16 bytes
     assert C.sizeof(engine.Options) == 32
     assert engine.RESULT_DTYPE.itemsize == 16
-    assert C.sizeof(engine.RunInfo) == 13 * 8
+    assert C.sizeof(engine.RunInfo) == 15 * 8
     assert C.sizeof(engine.Stats) == 8 * (2 + 256 + 4096 + 4096 + 8 + 1 + 1) + C.sizeof(engine.RunInfo)
 
 

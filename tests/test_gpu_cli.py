@@ -26,7 +26,7 @@ def test_heroam_cli_writes_reference_files(tmp_path, port, table):
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host")])
     conf_text = open(os.path.join(ROOT, "host", "config.example.conf")).read()
-    conf_text = conf_text.replace("number = 1000", "number = 40").replace("max_time = 10000000", "max_time = 20000")
+    conf_text = conf_text.replace("\nnumber = 1000", "\nnumber = 40").replace("max_time = 10000000", "max_time = 20000")
     (tmp_path / "run.conf").write_text(conf_text)
     r = subprocess.run([exe, "run.conf"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
