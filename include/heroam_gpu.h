@@ -53,7 +53,10 @@ enum {
    * dead zero-terms dropped), FMA contraction, hardware rsqrt: the counterpart of the
    * reference's own `-O3 -ffast-math -march=native` release build.  Agrees with the
    * strict reference within the tolerance stated in tests/test_gpu_parity.py. */
-  HEROAM_MODE_FAST = 1
+  HEROAM_MODE_FAST = 1,
+  /* The fast arithmetic without the folded constants of the hot kernels:
+   * same tolerance class, ~30 % more instructions; kept as a cross-check of HEROAM_MODE_FAST. */
+  HEROAM_MODE_FAST_PLAIN = 2
 };
 
 /* How a trajectory left the step loop (heroam_traj_result.status). */
@@ -71,10 +74,15 @@ typedef struct heroam_options {
   int mode;               /* HEROAM_MODE_*                                                 */
   unsigned int segment_steps; /* steps a trajectory runs between re-binning passes (0 = default) */
   unsigned long long max_steps; /* per-trajectory cap on loop iterations (0 = none)         */
-  int wide_kernel;        /* 0 = warp-per-trajectory kernel for > 8 moving particles (default);
-                             1 = the slow record-resident kernel (cross-check only)        */
+  int wide_kernel;        /* kernels for > 8 moving particles.  0 (default): register/shared-memory
+                             hybrid for 9..12, shared-memory kernel for 13..16, warp-per-trajectory
+                             above; 1 = the slow record-resident kernel (cross-check only);
+                             2 = warp-per-trajectory for everything above 8 (cross-check);
+                             3 = shared-memory kernel for 9..16 (cross-check)                  */
   unsigned int pool_slots; /* trajectories kept in flight by heroam_gpu_run_stats (0 = 2^20)        */
-  int reserved[2];
+  int count_work;         /* fast mode only: 1 = the integrate kernels also count in-range pair-steps
+                             (heroam_run_info.inrange_steps) at ~3 % cost; exact mode always counts   */
+  int reserved[1];
 } heroam_options;
 
 typedef struct heroam_traj_result {

@@ -42,7 +42,7 @@ def batch_with_n(n, m):
 
 peak = None
 for n in NS:
-    m = M if n <= 8 else max(148 * 16, M // 32)
+    m = M if n <= 8 else (148 * 256 if n <= 16 else max(148 * 16, M // 32))
     counts, flat = batch_with_n(n, m)
     conf = make_config(number=m, max_time=1e7)
     for mode in MODES:

@@ -12,6 +12,12 @@
 //           at most the sign of an exact zero, never a value.
 //   Fast  : same state and integrator; FMA contraction, closed-form pole image,
 //           MUFU rsqrt.  The GPU counterpart of the reference's -ffast-math build.
+//   Turbo : Fast with the loop-invariant factors folded into the state kept by the hot
+//           kernels (they hold w' = (dt/2) w and F' = (dt/2)^2/(m R^2) F and gather from a
+//           table pre-multiplied by that factor, so the half kick is a bare cross product and
+//           the orientation update needs no scaling), raw MUFU.RSQ, one-FMA table position,
+//           and optionally no work counting.  Used by the integrate kernels in fast mode;
+//           the once-per-pass resolve kernel keeps the plain Fast arithmetic.
 #pragma once
 
 #include <cstdint>
@@ -58,6 +64,11 @@ struct Consts {
   float far2;        // squared distance beyond which a pair can neither feel force nor meet (with margin)
   float kick;        // acc_scale * half_dt
   float radius2;     // 2 * radius
+  // Turbo folded constants
+  float kappa;       // acc_scale * half_dt^2 : force scale of the hot kernels' state and table copy
+  float inv_kappa;
+  float inv_half_dt;
+  float pos_bias;    // -grid_start * inv_grid
 };
 
 struct Counters {     // roofline work counters
@@ -71,7 +82,8 @@ struct Counters {     // roofline work counters
 
 struct DevView {       // everything a kernel needs, passed by value
   Consts c;
-  const float *__restrict__ table;
+  const float *__restrict__ table;    // grid_len + 1 entries, the last one 0 (out-of-table bin)
+  const float *__restrict__ table_k;  // the same multiplied by kappa (Turbo)
   heroam_particle *particles;
   TrajMeta *meta;
   uint32_t *act;       // act[first + s] = index (within the trajectory) of its s-th active particle
@@ -84,6 +96,8 @@ struct DevView {       // everything a kernel needs, passed by value
 // ---------------------------------------------------------------------------------
 struct Exact {
   static constexpr bool exact = true;
+  static constexpr bool turbo = false;
+  static constexpr bool count = true;
   __device__ __forceinline__ static float mul(float a, float b) { return __fmul_rn(a, b); }
   __device__ __forceinline__ static float add(float a, float b) { return __fadd_rn(a, b); }
   __device__ __forceinline__ static float sub(float a, float b) { return __fsub_rn(a, b); }
@@ -112,6 +126,8 @@ struct Exact {
 
 struct Fast {
   static constexpr bool exact = false;
+  static constexpr bool turbo = false;
+  static constexpr bool count = true;
   __device__ __forceinline__ static float mul(float a, float b) { return a * b; }
   __device__ __forceinline__ static float add(float a, float b) { return a + b; }
   __device__ __forceinline__ static float sub(float a, float b) { return a - b; }
@@ -131,6 +147,47 @@ struct Fast {
   }
 };
 
+struct Turbo : Fast {
+  static constexpr bool turbo = true;
+  static constexpr bool count = false;
+};
+struct TurboCount : Fast {
+  static constexpr bool turbo = true;
+  static constexpr bool count = true;
+};
+
+__device__ __forceinline__ float rsqrt_raw(float x) {  // one MUFU.RSQ, operands are never denormal here
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Conversions between the particle records (w, F) and the state a kernel keeps.
+template <class P>
+__device__ __forceinline__ void load_w(const Consts &c, const float *src, float w[3]) {
+  w[0] = P::turbo ? src[0] * c.half_dt : src[0];
+  w[1] = P::turbo ? src[1] * c.half_dt : src[1];
+  w[2] = P::turbo ? src[2] * c.half_dt : src[2];
+}
+template <class P>
+__device__ __forceinline__ void unscale_w(const Consts &c, const float w[3], float out[3]) {
+  out[0] = P::turbo ? w[0] * c.inv_half_dt : w[0];
+  out[1] = P::turbo ? w[1] * c.inv_half_dt : w[1];
+  out[2] = P::turbo ? w[2] * c.inv_half_dt : w[2];
+}
+template <class P>
+__device__ __forceinline__ void load_f(const Consts &c, const float *src, float f[3]) {
+  f[0] = P::turbo ? src[0] * c.kappa : src[0];
+  f[1] = P::turbo ? src[1] * c.kappa : src[1];
+  f[2] = P::turbo ? src[2] * c.kappa : src[2];
+}
+template <class P>
+__device__ __forceinline__ void unscale_f(const Consts &c, const float f[3], float out[3]) {
+  out[0] = P::turbo ? f[0] * c.inv_kappa : f[0];
+  out[1] = P::turbo ? f[1] * c.inv_kappa : f[1];
+  out[2] = P::turbo ? f[2] * c.inv_kappa : f[2];
+}
+
 // ---------------------------------------------------------------------------------
 // per-particle pieces of a step
 // ---------------------------------------------------------------------------------
@@ -147,6 +204,8 @@ __device__ __forceinline__ void half_kick(const Consts &c, const float r[3], con
     hk[0] = P::mul(P::mul(tx, c.acc_scale), c.half_dt);
     hk[1] = P::mul(P::mul(ty, c.acc_scale), c.half_dt);
     hk[2] = P::mul(P::mul(tz, c.acc_scale), c.half_dt);
+  } else if (P::turbo) {  // F' already carries (dt/2)^2/(m R^2): this is (dt/2) * (half kick)
+    hk[0] = tx; hk[1] = ty; hk[2] = tz;
   } else {
     hk[0] = tx * c.kick;
     hk[1] = ty * c.kick;
@@ -175,6 +234,18 @@ __device__ __forceinline__ void advance_orientation(const Consts &c, const float
     float nz = P::add(qz, P::mul(tz, c.half_dt));
     const float inv = __frcp_rn(__fsqrt_rn(P::dot4(na, nx, ny, nz)));
     q[0] = P::mul(na, inv); q[1] = P::mul(nx, inv); q[2] = P::mul(ny, inv); q[3] = P::mul(nz, inv);
+  } else if (P::turbo) {
+    // w' = (dt/2) w.  The increment w' (x) q (~1e-6 |q|) is formed on its own, at full relative
+    // precision, and added to q with ONE rounding, exactly as the reference does: accumulating
+    // the three products straight into q would round three times per step at ulp(q) and
+    // quadruple the random walk of the orientation (measured: 1.6e-3 A instead of 4e-4 A after
+    // 2000 steps on R = 47.8 A).
+    const float na = qa - fmaf(oz, qz, fmaf(oy, qy, ox * qx));
+    const float nx = qx + fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
+    const float ny = qy + fmaf(oz, qx, fmaf(-ox, qz, oy * qa));
+    const float nz = qz + fmaf(oz, qa, fmaf(-oy, qx, ox * qy));
+    const float inv = rsqrt_raw(fmaf(nz, nz, fmaf(ny, ny, fmaf(nx, nx, na * na))));
+    q[0] = na * inv; q[1] = nx * inv; q[2] = ny * inv; q[3] = nz * inv;
   } else {
     const float ta = -fmaf(oz, qz, fmaf(oy, qy, ox * qx));
     const float tx = fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
@@ -206,6 +277,10 @@ __device__ __forceinline__ void pole_position(const Consts &c, const float q[4],
     r[0] = P::mul(rx, c.radius);
     r[1] = P::mul(ry, c.radius);
     r[2] = P::mul(rz, c.radius);
+  } else if (P::turbo) {  // unit q: a^2 - x^2 - y^2 + z^2 = 1 - 2 (x^2 + y^2)
+    r[0] = c.radius2 * fmaf(nx, nz, na * ny);
+    r[1] = c.radius2 * fmaf(ny, nz, -(na * nx));
+    r[2] = fmaf(-c.radius2, fmaf(nx, nx, ny * ny), c.radius);
   } else {
     // unit q: q (0,0,1) q^-1 = (2(xz + ay), 2(yz - ax), a^2 - x^2 - y^2 + z^2)
     r[0] = c.radius2 * fmaf(nx, nz, na * ny);
@@ -231,10 +306,11 @@ __device__ __forceinline__ float pair_force(const Consts &c, const float *__rest
   const float dy = P::sub(rj[1], rk[1]);
   const float dz = P::sub(rj[2], rk[2]);
   const float d = P::dot3(dx, dy, dz);
-  // bin = (int)((d - start) * inv_grid) in float, as the reference (Q6)
+  // bin = (int)((d - start) * inv_grid) in float, as the reference (Q6); a negative or too
+  // large bin means "outside the table"
   const float pos = __fmul_rn(__fsub_rn(d, c.grid_start), c.inv_grid);
-  const int bin = __float2int_rz(pos);
-  if (pos > -1.0f && bin < c.grid_len) {
+  const unsigned bin = (unsigned)__float2int_rz(pos);
+  if (bin < (unsigned)c.grid_len) {
     ++inrange;
     const float tv = __ldg(table + bin);
     float scale;
@@ -262,8 +338,8 @@ __device__ __forceinline__ float pair_force(const Consts &c, const float *__rest
 // leaves every value as the reference's "skip" does.
 struct PairGeom {
   float dx, dy, dz, d;
-  int bin;      // valid table index (0 when the pair is outside the table)
-  bool inside;
+  unsigned bin;  // table index, clamped to grid_len (the zero entry appended to the table) when outside
+  bool inside;   // only maintained when the policy counts work
 };
 
 template <class P>
@@ -273,21 +349,26 @@ __device__ __forceinline__ PairGeom pair_geom(const Consts &c, const float rj[3]
   g.dy = P::sub(rj[1], rk[1]);
   g.dz = P::sub(rj[2], rk[2]);
   g.d = P::dot3(g.dx, g.dy, g.dz);
-  const float pos = __fmul_rn(__fsub_rn(g.d, c.grid_start), c.inv_grid);  // float, as the reference (Q6)
-  const int bin = __float2int_rz(pos);
-  g.inside = pos > -1.0f && bin < c.grid_len;
-  g.bin = g.inside ? bin : 0;
+  // Exact / Fast: (d - start) * inv_grid in float exactly as the reference (Q6).  The float ->
+  // int conversion truncates (a position in (-1, 0) is bin 0, as in the reference); seen as
+  // unsigned, a negative bin is huge, so one unsigned min sends both sides of the table to
+  // the appended zero entry.
+  const float pos = P::turbo ? fmaf(g.d, c.inv_grid, c.pos_bias) : __fmul_rn(__fsub_rn(g.d, c.grid_start), c.inv_grid);
+  g.bin = min((unsigned)__float2int_rz(pos), (unsigned)c.grid_len);
+  g.inside = P::count ? g.bin < (unsigned)c.grid_len : false;
   return g;
 }
 
-__device__ __forceinline__ float pair_gather(const float *__restrict__ table, const PairGeom &g) {
-  const float tv = __ldg(table + g.bin);
-  return g.inside ? tv : 0.0f;
+// the table value (0 outside the table); Turbo reads the copy scaled by kappa
+template <class P>
+__device__ __forceinline__ float pair_gather(const DevView &v, const PairGeom &g) {
+  return __ldg((P::turbo ? v.table_k : v.table) + g.bin);
 }
 
 template <class P>
 __device__ __forceinline__ float pair_scale(float tv, float d) {
   if (P::exact) return __double2float_rn(__ddiv_rn((double)tv, __dsqrt_rn((double)d)));
+  if (P::turbo) return tv * rsqrt_raw(d);
   return tv * rsqrtf(d);
 }
 

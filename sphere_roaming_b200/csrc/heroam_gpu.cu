@@ -44,7 +44,9 @@ struct heroam_ctx {
   cudaEvent_t bin_done[N_BINS] = {};
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_i0 = nullptr, ev_i1 = nullptr, ev_c0 = nullptr,
               ev_c1 = nullptr;
-  float *d_table = nullptr;
+  float *d_table = nullptr;    // table_len + 1 floats: the table and a trailing 0 (the out-of-table bin)
+  float *d_table_k = nullptr;  // the same multiplied by table_kappa (Turbo kernels)
+  float table_kappa = 0.0f;
   long table_len = 0;
   // batch buffers (grown on demand)
   heroam_particle *d_particles = nullptr;
@@ -119,6 +121,10 @@ static int make_consts(const heroam_config &conf, unsigned long long he_number, 
     c.far2 = (float)(reach2 * 1.0001 + 1.0e-3);
   }
   c.kick = c.acc_scale * c.half_dt;
+  c.kappa = c.kick * c.half_dt;
+  c.inv_kappa = 1.0f / c.kappa;
+  c.inv_half_dt = 1.0f / c.half_dt;
+  c.pos_bias = -c.grid_start * c.inv_grid;
   c.radius2 = 2.0f * c.radius;
   *out = c;
   return HEROAM_OK;
@@ -144,7 +150,7 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   ctx->conf = *conf;
   memset(&ctx->opt, 0, sizeof ctx->opt);
   if (opt) ctx->opt = *opt;
-  if (ctx->opt.mode != HEROAM_MODE_EXACT && ctx->opt.mode != HEROAM_MODE_FAST) {
+  if (ctx->opt.mode != HEROAM_MODE_EXACT && ctx->opt.mode != HEROAM_MODE_FAST && ctx->opt.mode != HEROAM_MODE_FAST_PLAIN) {
     delete ctx;
     return fail(HEROAM_E_ARG, "unknown mode %d", opt->mode);
   }
@@ -163,7 +169,9 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   CU(cudaEventCreate(&ctx->ev_i1));
   CU(cudaEventCreate(&ctx->ev_c0));
   CU(cudaEventCreate(&ctx->ev_c1));
-  CU(cudaMalloc(&ctx->d_table, (size_t)ctx->table_len * sizeof(float)));
+  CU(cudaMalloc(&ctx->d_table, ((size_t)ctx->table_len + 1) * sizeof(float)));
+  CU(cudaMalloc(&ctx->d_table_k, ((size_t)ctx->table_len + 1) * sizeof(float)));
+  CU(cudaMemset(ctx->d_table, 0, ((size_t)ctx->table_len + 1) * sizeof(float)));
   CU(cudaMemcpy(ctx->d_table, force_list, (size_t)ctx->table_len * sizeof(float), cudaMemcpyHostToDevice));
   CU(cudaMalloc(&ctx->d_bin_count, N_BINS * sizeof(uint32_t)));
   CU(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
@@ -178,6 +186,7 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   cudaFree(ctx->d_table);
+  cudaFree(ctx->d_table_k);
   cudaFree(ctx->d_particles);
   cudaFree(ctx->d_meta);
   cudaFree(ctx->d_act);
@@ -203,7 +212,8 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
 
 extern "C" int heroam_gpu_set_mode(heroam_ctx *ctx, int mode) {
   if (!ctx) return fail(HEROAM_E_ARG, "null context");
-  if (mode != HEROAM_MODE_EXACT && mode != HEROAM_MODE_FAST) return fail(HEROAM_E_ARG, "unknown mode %d", mode);
+  if (mode != HEROAM_MODE_EXACT && mode != HEROAM_MODE_FAST && mode != HEROAM_MODE_FAST_PLAIN)
+    return fail(HEROAM_E_ARG, "unknown mode %d", mode);
   ctx->opt.mode = mode;
   return HEROAM_OK;
 }
@@ -249,6 +259,7 @@ static DevView make_view(heroam_ctx *ctx, const Consts &c) {
   DevView v;
   v.c = c;
   v.table = ctx->d_table;
+  v.table_k = ctx->d_table_k;
   v.particles = ctx->d_particles;
   v.meta = ctx->d_meta;
   v.act = ctx->d_act;
@@ -291,6 +302,17 @@ extern "C" int heroam_gpu_upload(heroam_ctx *ctx, unsigned long long he_number, 
   return HEROAM_OK;
 }
 
+// the kappa-scaled copy of the table the Turbo kernels gather from
+static int refresh_scaled_table(heroam_ctx *ctx, const Consts &c) {
+  if (ctx->table_kappa == c.kappa) return HEROAM_OK;
+  const unsigned n = (unsigned)ctx->table_len + 1u;
+  k_scale_table<<<(n + 255u) / 256u, 256, 0, ctx->main>>>(ctx->d_table_k, ctx->d_table, n, c.kappa);
+  CU(cudaGetLastError());
+  ctx->table_kappa = c.kappa;
+  ctx->info.kernel_launches++;
+  return HEROAM_OK;
+}
+
 template <class P>
 static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) {
   const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
@@ -312,10 +334,30 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) 
     case 8: k_integrate_thread<8, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
     default: {
       const unsigned wgrid = (cnt + WARP_KERNEL_WARPS - 1) / WARP_KERNEL_WARPS;
-      if (ctx->opt.wide_kernel == 1) k_integrate_records<P><<<(cnt + 63) / 64, 64, 0, s>>>(v, list, cnt);
-      else if (bin == BIN_WARP1) k_integrate_warp<1, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
-      else if (bin == BIN_WARP2) k_integrate_warp<2, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
-      else k_integrate_warp<4, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+      const unsigned sgrid = (cnt + SMEM_TPB - 1) / SMEM_TPB;
+      if (ctx->opt.wide_kernel == 1) {
+        k_integrate_records<P><<<(cnt + 63) / 64, 64, 0, s>>>(v, list, cnt);
+#define HEROAM_HYBRID_CASE(A)                                                                                     \
+  } else if (bin == A && ctx->opt.wide_kernel == 0) {                                                             \
+    CU(cudaFuncSetAttribute(k_integrate_hybrid<A, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                            (int)hybrid_smem_bytes<A>()));                                                        \
+    k_integrate_hybrid<A, P><<<sgrid, SMEM_TPB, hybrid_smem_bytes<A>(), s>>>(v, list, cnt);
+      HEROAM_HYBRID_CASE(9)
+      HEROAM_HYBRID_CASE(10)
+      HEROAM_HYBRID_CASE(11)
+      HEROAM_HYBRID_CASE(12)
+#undef HEROAM_HYBRID_CASE
+      } else if (bin <= BIN_SMEM16 && ctx->opt.wide_kernel != 2) {
+        const size_t bytes = 5ull * 16 * SMEM_TPB * sizeof(float4);
+        CU(cudaFuncSetAttribute(k_integrate_smem<16, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        k_integrate_smem<16, P><<<sgrid, SMEM_TPB, bytes, s>>>(v, list, cnt);
+      } else if (bin <= BIN_WARP1) {
+        k_integrate_warp<1, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+      } else if (bin == BIN_WARP2) {
+        k_integrate_warp<2, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+      } else {
+        k_integrate_warp<4, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+      }
       break;
     }
   }
@@ -323,9 +365,14 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) 
   return HEROAM_OK;
 }
 
-template <class P>
+// R: arithmetic of the once-per-pass resolve kernel; H: arithmetic of the integrate kernels
+template <class R, class H>
 static int run_passes(heroam_ctx *ctx, const Consts &c) {
   DevView v = make_view(ctx, c);
+  if (H::turbo) {
+    int rc = refresh_scaled_table(ctx, c);
+    if (rc) return rc;
+  }
   const uint32_t n = ctx->n_traj;
   const unsigned tgrid = (n + 127) / 128;
   const uint32_t cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu
@@ -343,7 +390,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     Segments sg = make_segments(ctx->opt.segment_steps);
     sg.free_stride = ctx->free_stride;
     sg.drain = draining ? 1u : 0u;
-    k_resolve_and_bin<P><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
+    k_resolve_and_bin<R><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
@@ -370,7 +417,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
       if (!cnt) continue;
       // the bin streams start after ev_i0, i.e. after this pass's resolve kernel
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<P>(ctx, v, b, cnt);
+      int rc = launch_bin<H>(ctx, v, b, cnt);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
@@ -411,7 +458,10 @@ extern "C" int heroam_gpu_run(heroam_ctx *ctx) {
   if (rc) return rc;
   ctx->uploaded = false;  // the resident batch is consumed
   if (ctx->n_traj == 0) return HEROAM_OK;
-  rc = ctx->opt.mode == HEROAM_MODE_EXACT ? run_passes<Exact>(ctx, c) : run_passes<Fast>(ctx, c);
+  rc = ctx->opt.mode == HEROAM_MODE_EXACT        ? run_passes<Exact, Exact>(ctx, c)
+       : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN ? run_passes<Fast, Fast>(ctx, c)
+       : ctx->opt.count_work                     ? run_passes<Fast, TurboCount>(ctx, c)
+                                                 : run_passes<Fast, Turbo>(ctx, c);
   return rc;
 }
 

@@ -20,22 +20,28 @@
 
 namespace heroam {
 
-constexpr int THREAD_MAX_A = 8;   // bins 1..8: k_integrate_thread<A>, one thread per trajectory
-constexpr int BIN_WARP1 = 9;      // 9..32 active: k_integrate_warp<1>, one warp per trajectory
-constexpr int BIN_WARP2 = 10;     // 33..64 active: k_integrate_warp<2> (two particles per lane)
-constexpr int BIN_WARP4 = 11;     // 65..128 active: k_integrate_warp<4>
+// Bins: a live trajectory is binned by the number of its particles still moving.
+constexpr int THREAD_MAX_A = 8;   // bins 1..8  : k_integrate_thread<A>, one thread per trajectory, all state in registers
+constexpr int HYBRID_MAX_A = 12;  // bins 9..12 : k_integrate_hybrid<A>, one thread per trajectory, positions and forces in
+                                  //              registers, orientation / angular velocities in shared memory
+constexpr int BIN_SMEM16 = 13;    // 13..16 active: k_integrate_smem<16>, one thread per trajectory, state in shared memory
+constexpr int BIN_WARP1 = 14;     // 17..32 active: k_integrate_warp<1>, one warp per trajectory
+constexpr int BIN_WARP2 = 15;     // 33..64 active: k_integrate_warp<2> (two particles per lane)
+constexpr int BIN_WARP4 = 16;     // 65..128 active: k_integrate_warp<4>
 // every pair provably out of reach for a whole segment: k_free_flight, one thread per PARTICLE.
 // Three tiers of FIXED segment length (so that all lanes of a warp run the same trip count):
-constexpr int BIN_FREE = 12;      // BIN_FREE + 0: short, + 1: medium, + 2: long
+constexpr int BIN_FREE = 17;      // BIN_FREE + 0: short, + 1: medium, + 2: long
 constexpr int N_FREE_TIERS = 3;
 constexpr int N_BINS = BIN_FREE + N_FREE_TIERS;
 constexpr int FREE_MAX_A = 8;     // the free-flight analysis is done for trajectories with <= 8 moving particles
 constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
 constexpr int INTEGRATE_TPB = 128;
+constexpr int SMEM_TPB = 64;          // threads (= trajectories) per block of k_integrate_smem / k_integrate_hybrid
 constexpr int WARP_KERNEL_WARPS = 4;  // warps (= trajectories) per block of k_integrate_warp
 
 __host__ __device__ inline int bin_of(uint32_t active) {
-  if (active <= (uint32_t)THREAD_MAX_A) return (int)active;
+  if (active <= (uint32_t)HYBRID_MAX_A) return (int)active;
+  if (active <= 16u) return BIN_SMEM16;
   if (active <= 32u) return BIN_WARP1;
   if (active <= 64u) return BIN_WARP2;
   return BIN_WARP4;
@@ -52,6 +58,49 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---------------------------------------------------------------------------------
+// Record formats written by the integrate kernels (w, wh, f are in the kernel's state
+// units: see load_w / load_f).
+// ---------------------------------------------------------------------------------
+// A step abandoned after the drift because a pair came within icd_dist (see finish_step).
+template <class P>
+__device__ __forceinline__ void write_midstep(const Consts &c, heroam_particle *p, const float q[4], const float r[3],
+                                              const float w[3], const float wh[3], const float r_old[3], float time,
+                                              bool stepped_before) {
+  float w_rec[3], wh_rec[3];
+  unscale_w<P>(c, w, w_rec);
+  unscale_w<P>(c, wh, wh_rec);
+  p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
+  st3(p->position, r);
+  st3(p->ang_velocity, w_rec);  // w(t): what a particle frozen in this step keeps
+  st3(p->force, wh_rec);        // scratch: w(t + dt/2)
+  p->time = time;
+  if (stepped_before) {         // else the imported velocity fields stand
+    float vel[3], v2;
+    stored_velocity<P>(r_old, w_rec, vel, v2);
+    st3(p->velocity, vel);
+    p->velocity_sq = v2;
+  }
+}
+// Clean state at a step boundary, every field as the reference holds it.
+template <class P>
+__device__ __forceinline__ void write_clean(const Consts &c, heroam_particle *p, const float q[4], const float r[3],
+                                            const float w[3], const float f[3], float time, bool has_force_mag) {
+  float w_rec[3], f_rec[3], vel[3], v2;
+  unscale_w<P>(c, w, w_rec);
+  unscale_f<P>(c, f, f_rec);
+  p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
+  st3(p->position, r);
+  st3(p->ang_velocity, w_rec);
+  st3(p->force, f_rec);
+  stored_velocity<P>(r, w_rec, vel, v2);
+  st3(p->velocity, vel);
+  p->velocity_sq = v2;
+  p->time = time;
+  // force_mag only exists for indices below no - 1 (simulation.c:205, :232; Q9)
+  p->force_mag = has_force_mag ? vec_norm(f_rec) : 0.0f;
 }
 
 // ---------------------------------------------------------------------------------
@@ -225,7 +274,9 @@ __host__ inline Segments make_segments(uint32_t base) {
   sg.of_bin[3] = sg.of_bin[4] = base;
   sg.of_bin[5] = sg.of_bin[6] = scaled(1, 2);
   sg.of_bin[7] = sg.of_bin[8] = scaled(1, 4);
-  sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 4);
+  for (int b = THREAD_MAX_A + 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(1, 8);
+  sg.of_bin[BIN_SMEM16] = scaled(1, 8);
+  sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
   sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
   sg.of_bin[BIN_FREE + 1] = scaled(2, 1);
   sg.of_bin[BIN_FREE + 2] = scaled(16, 1);
@@ -397,8 +448,9 @@ __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__r
   const TrajMeta m = v.meta[e.x];  // read only: the next resolve pass commits steps and time
   heroam_particle *p = v.particles + m.first + v.act[m.first + e.y];
   float q[4] = {p->orientation[0], p->orientation[1], p->orientation[2], p->orientation[3]};
-  float w[3];
-  ld3(p->ang_velocity, w);
+  float w[3], w_rec[3];
+  ld3(p->ang_velocity, w_rec);
+  load_w<P>(c, w_rec, w);
   float time = m.time;
   for (uint32_t k = m.steps; k < m.step_stop; ++k) {
     advance_orientation<P>(c, w, q);
@@ -406,7 +458,7 @@ __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__r
   }
   float r[3], vel[3], v2;
   pole_position<P>(c, q, r);
-  stored_velocity<P>(r, w, vel, v2);
+  stored_velocity<P>(r, w_rec, vel, v2);
   p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
   st3(p->position, r);
   st3(p->velocity, vel);
@@ -435,8 +487,8 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
       q[s][0] = p->orientation[0]; q[s][1] = p->orientation[1];
       q[s][2] = p->orientation[2]; q[s][3] = p->orientation[3];
       ld3(p->position, r[s]);
-      ld3(p->ang_velocity, w[s]);
-      ld3(p->force, f[s]);
+      load_w<P>(c, p->ang_velocity, w[s]);
+      load_f<P>(c, p->force, f[s]);
       half_kick<P>(c, r[s], f[s], hk[s]);
     }
     uint32_t steps = m.steps;
@@ -465,9 +517,9 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
 #pragma unroll
         for (int k = j + 1; k < A; ++k) {
           g[k] = pair_geom<P>(c, r[j], r[k]);
-          tv[k] = pair_gather(v.table, g[k]);
+          tv[k] = pair_gather<P>(v, g[k]);
           dmin = fminf(dmin, g[k].d);
-          in_step += g[k].inside ? 1u : 0u;
+          if (P::count) in_step += g[k].inside ? 1u : 0u;
         }
 #pragma unroll
         for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
@@ -487,42 +539,14 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
     }
     done_steps = steps - m.steps;
     if (met) {
-      // hand the half-done step to k_resolve_and_bin (format: see finish_step)
 #pragma unroll
-      for (int s = 0; s < A; ++s) {
-        heroam_particle *p = rec[s];
-        p->orientation[0] = q[s][0]; p->orientation[1] = q[s][1];
-        p->orientation[2] = q[s][2]; p->orientation[3] = q[s][3];
-        st3(p->position, r[s]);
-        st3(p->ang_velocity, w[s]);
-        st3(p->force, wh[s]);
-        p->time = time;
-        if (steps > 0) {
-          float vel[3], v2;
-          stored_velocity<P>(r_old[s], w[s], vel, v2);
-          st3(p->velocity, vel);
-          p->velocity_sq = v2;
-        }
-      }
+      for (int s = 0; s < A; ++s) write_midstep<P>(c, rec[s], q[s], r[s], w[s], wh[s], r_old[s], time, steps > 0);
       m.status = ST_MIDSTEP;
     } else if (done_steps > 0) {
-      // clean state at a step boundary, every field as the reference holds it
 #pragma unroll
       for (int s = 0; s < A; ++s) {
-        heroam_particle *p = rec[s];
-        p->orientation[0] = q[s][0]; p->orientation[1] = q[s][1];
-        p->orientation[2] = q[s][2]; p->orientation[3] = q[s][3];
-        st3(p->position, r[s]);
-        st3(p->ang_velocity, w[s]);
-        st3(p->force, f[s]);
-        float vel[3], v2;
-        stored_velocity<P>(r[s], w[s], vel, v2);
-        st3(p->velocity, vel);
-        p->velocity_sq = v2;
-        p->time = time;
-        // force_mag only exists for indices below no - 1 (:205, :232; Q9)
-        const uint32_t j = (uint32_t)(p - (v.particles + m.first));
-        p->force_mag = (j + 1u < m.no) ? vec_norm(f[s]) : 0.0f;
+        const uint32_t j = (uint32_t)(rec[s] - (v.particles + m.first));
+        write_clean<P>(c, rec[s], q[s], r[s], w[s], f[s], time, j + 1u < m.no);
       }
     }
     m.steps = steps;
@@ -535,6 +559,256 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
     atomicAdd(&v.counters->particle_steps, ds * A);
     atomicAdd(&v.counters->pair_steps, ds * (A * (A - 1) / 2));
     atomicAdd(&v.counters->inrange_steps, ir);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_integrate_hybrid<A>, A = 9..12: one thread per trajectory.  Positions and forces (the
+// operands of the A(A-1)/2-pair loop, which dominates at this size) stay in registers and
+// the pair loop is fully unrolled exactly as in k_integrate_thread; what is touched only
+// once per particle and step -- orientation, angular velocity, its half-step value and the
+// pre-drift position kept for a possible meeting -- lives in the thread's private column
+// of shared memory, [array][particle][thread]:
+//     qs = orientation     ws = (w.xyz, r_old.x)     hs = (w(t+dt/2).xyz, r_old.y)     zs = r_old.z
+// Same operations in the same order as the register kernels: bit-identical results.
+// ---------------------------------------------------------------------------------
+template <int A>
+constexpr size_t hybrid_smem_bytes() { return (size_t)A * SMEM_TPB * (3 * sizeof(float4) + sizeof(float)); }
+
+template <int A, class P>
+__global__ void __launch_bounds__(SMEM_TPB) k_integrate_hybrid(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
+  extern __shared__ float4 sm4[];
+  const uint32_t tid = threadIdx.x;
+  float4 *qs = sm4 + tid, *ws = qs + A * SMEM_TPB, *hs = ws + A * SMEM_TPB;
+  float *zs = reinterpret_cast<float *>(sm4 + 3 * A * SMEM_TPB) + tid;
+  const uint32_t item = blockIdx.x * SMEM_TPB + tid;
+  unsigned long long done_steps = 0, inrange_total = 0;
+  if (item < count) {
+    const Consts &c = v.c;
+    const uint32_t t = list[item];
+    TrajMeta m = v.meta[t];
+    heroam_particle *base = v.particles + m.first;
+    const uint32_t *act = v.act + m.first;
+    float r[A][3], f[A][3];
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      const heroam_particle *p = base + act[s];
+      qs[s * SMEM_TPB] = make_float4(p->orientation[0], p->orientation[1], p->orientation[2], p->orientation[3]);
+      float w0[3];
+      load_w<P>(c, p->ang_velocity, w0);
+      ws[s * SMEM_TPB] = make_float4(w0[0], w0[1], w0[2], 0.0f);
+      ld3(p->position, r[s]);
+      load_f<P>(c, p->force, f[s]);
+    }
+    uint32_t steps = m.steps;
+    float time = m.time;
+    bool met = false;
+    while (steps < m.step_stop) {
+#pragma unroll
+      for (int s = 0; s < A; ++s) {
+        const float4 w4 = ws[s * SMEM_TPB], q4 = qs[s * SMEM_TPB];
+        float hk[3], wh[3], q[4] = {q4.x, q4.y, q4.z, q4.w};
+        half_kick<P>(c, r[s], f[s], hk);
+        wh[0] = P::add(w4.x, hk[0]); wh[1] = P::add(w4.y, hk[1]); wh[2] = P::add(w4.z, hk[2]);
+        ws[s * SMEM_TPB] = make_float4(w4.x, w4.y, w4.z, r[s][0]);
+        hs[s * SMEM_TPB] = make_float4(wh[0], wh[1], wh[2], r[s][1]);
+        zs[s * SMEM_TPB] = r[s][2];
+        drift<P>(c, wh, q, r[s]);
+        qs[s * SMEM_TPB] = make_float4(q[0], q[1], q[2], q[3]);
+        f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
+      }
+      float dmin = 3.0e38f;
+      uint32_t in_step = 0;
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) {
+        PairGeom g[A];
+        float tv[A];
+#pragma unroll
+        for (int k = j + 1; k < A; ++k) {
+          g[k] = pair_geom<P>(c, r[j], r[k]);
+          tv[k] = pair_gather<P>(v, g[k]);
+          dmin = fminf(dmin, g[k].d);
+          if (P::count) in_step += g[k].inside ? 1u : 0u;
+        }
+#pragma unroll
+        for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
+      }
+      if (dmin < c.icd2) { met = true; break; }
+#pragma unroll
+      for (int s = 0; s < A; ++s) {
+        const float4 h4 = hs[s * SMEM_TPB];
+        float hk[3];
+        half_kick<P>(c, r[s], f[s], hk);
+        ws[s * SMEM_TPB] = make_float4(P::add(h4.x, hk[0]), P::add(h4.y, hk[1]), P::add(h4.z, hk[2]), 0.0f);
+      }
+      time = __fadd_rn(time, c.dt);
+      ++steps;
+      inrange_total += in_step;
+    }
+    done_steps = steps - m.steps;
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      heroam_particle *p = base + act[s];
+      const float4 q4 = qs[s * SMEM_TPB], w4 = ws[s * SMEM_TPB];
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w}, w[3] = {w4.x, w4.y, w4.z};
+      if (met) {
+        const float4 h4 = hs[s * SMEM_TPB];
+        const float wh[3] = {h4.x, h4.y, h4.z}, r_old[3] = {w4.w, h4.w, zs[s * SMEM_TPB]};
+        write_midstep<P>(c, p, q, r[s], w, wh, r_old, time, steps > 0);
+      } else if (done_steps > 0) {
+        write_clean<P>(c, p, q, r[s], w, f[s], time, act[s] + 1u < m.no);
+      }
+    }
+    if (met) m.status = ST_MIDSTEP;
+    m.steps = steps;
+    m.time = time;
+    v.meta[t] = m;
+  }
+  if (done_steps) {
+    atomicAdd(&v.counters->particle_steps, done_steps * A);
+    atomicAdd(&v.counters->pair_steps, done_steps * (A * (A - 1) / 2));
+    atomicAdd(&v.counters->inrange_steps, inrange_total);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_integrate_smem<CAP>: one thread per trajectory with 9..CAP moving particles.  Too many
+// for registers, so the per-particle state lives in the thread's private column of shared
+// memory, five float4 per particle laid out [array][particle][thread] (consecutive threads
+// -> consecutive 16-byte words: conflict-free 128-bit accesses):
+//     pos = (r.xyz, r_old.x)   frc = (F.xyz, r_old.y)   w = (w.xyz, r_old.z)
+//     q   = orientation        wh  = (w(t + dt/2), -)
+// Loops are rolled (any 9 <= a <= CAP), the pair loop is the reference's (j,k) order and the
+// accumulators start from the value already in memory, so results are bit-identical to the
+// register kernels.  Compared with the warp-per-trajectory kernel every pair is evaluated
+// once and no lane idles.
+// ---------------------------------------------------------------------------------
+template <int CAP, class P>
+__global__ void __launch_bounds__(SMEM_TPB) k_integrate_smem(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
+  extern __shared__ float4 sm4[];
+  const uint32_t tid = threadIdx.x;
+  float4 *pos = sm4 + tid, *frc = pos + CAP * SMEM_TPB, *qq = frc + CAP * SMEM_TPB, *ww = qq + CAP * SMEM_TPB,
+         *whh = ww + CAP * SMEM_TPB;
+#define COL(arr, s) (arr)[(s) * SMEM_TPB]
+  const uint32_t item = blockIdx.x * SMEM_TPB + tid;
+  unsigned long long done_steps = 0, inrange_total = 0;
+  uint32_t a = 0;
+  if (item < count) {
+    const Consts &c = v.c;
+    const uint32_t t = list[item];
+    TrajMeta m = v.meta[t];
+    a = m.n_active;
+    heroam_particle *base = v.particles + m.first;
+    const uint32_t *act = v.act + m.first;
+    for (uint32_t s = 0; s < a; ++s) {
+      const heroam_particle *p = base + act[s];
+      COL(qq, s) = make_float4(p->orientation[0], p->orientation[1], p->orientation[2], p->orientation[3]);
+      COL(pos, s) = make_float4(p->position[0], p->position[1], p->position[2], 0.0f);
+      float w0[3], f0[3];
+      load_w<P>(c, p->ang_velocity, w0);
+      load_f<P>(c, p->force, f0);
+      COL(ww, s) = make_float4(w0[0], w0[1], w0[2], 0.0f);
+      COL(frc, s) = make_float4(f0[0], f0[1], f0[2], 0.0f);
+    }
+    uint32_t steps = m.steps;
+    float time = m.time;
+    bool met = false;
+    while (steps < m.step_stop) {
+      // first half kick + drift
+#pragma unroll 2
+      for (uint32_t s = 0; s < a; ++s) {
+        const float4 r4 = COL(pos, s), f4 = COL(frc, s), q4 = COL(qq, s), w4 = COL(ww, s);
+        const float r[3] = {r4.x, r4.y, r4.z}, f[3] = {f4.x, f4.y, f4.z};
+        float hk[3], wh[3], q[4] = {q4.x, q4.y, q4.z, q4.w}, rn[3];
+        half_kick<P>(c, r, f, hk);
+        wh[0] = P::add(w4.x, hk[0]); wh[1] = P::add(w4.y, hk[1]); wh[2] = P::add(w4.z, hk[2]);
+        drift<P>(c, wh, q, rn);
+        COL(qq, s) = make_float4(q[0], q[1], q[2], q[3]);
+        COL(pos, s) = make_float4(rn[0], rn[1], rn[2], r4.x);
+        COL(frc, s) = make_float4(0.0f, 0.0f, 0.0f, r4.y);
+        COL(ww, s) = make_float4(w4.x, w4.y, w4.z, r4.z);
+        COL(whh, s) = make_float4(wh[0], wh[1], wh[2], 0.0f);
+      }
+      // all pairs, (j,k) order
+      float dmin = 3.0e38f;
+      uint32_t in_step = 0;
+      for (uint32_t j = 0; j + 1 < a; ++j) {
+        const float4 rj4 = COL(pos, j);
+        float4 fj4 = COL(frc, j);
+        const float rj[3] = {rj4.x, rj4.y, rj4.z};
+        float fj[3] = {fj4.x, fj4.y, fj4.z};
+        // partners four at a time: all loads, then geometry and gathers, then the ordered
+        // accumulation, then all stores -- so that four pairs are in flight together
+        for (uint32_t k0 = j + 1; k0 < a; k0 += 4) {
+          float4 rk4[4], fk4[4];
+          PairGeom g[4];
+          float tv[4];
+          bool valid[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            valid[u] = k0 + u < a;
+            const uint32_t kk = valid[u] ? k0 + u : a - 1u;
+            rk4[u] = COL(pos, kk);
+            fk4[u] = COL(frc, kk);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float rk[3] = {rk4[u].x, rk4[u].y, rk4[u].z};
+            g[u] = pair_geom<P>(c, rj, rk);
+            if (!valid[u]) { g[u].bin = (unsigned)c.grid_len; g[u].inside = false; }  // the zero entry
+            tv[u] = pair_gather<P>(v, g[u]);
+            dmin = fminf(dmin, valid[u] ? g[u].d : 3.0e38f);
+            if (P::count) in_step += g[u].inside ? 1u : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float fk[3] = {fk4[u].x, fk4[u].y, fk4[u].z};
+            pair_apply<P>(pair_scale<P>(tv[u], g[u].d), g[u], fj, fk);  // an invalid slot adds +-0 to fj
+            fk4[u] = make_float4(fk[0], fk[1], fk[2], fk4[u].w);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (valid[u]) COL(frc, k0 + u) = fk4[u];
+        }
+        COL(frc, j) = make_float4(fj[0], fj[1], fj[2], fj4.w);
+      }
+      if (dmin < c.icd2) { met = true; break; }
+      // second half kick
+#pragma unroll 2
+      for (uint32_t s = 0; s < a; ++s) {
+        const float4 r4 = COL(pos, s), f4 = COL(frc, s), wh4 = COL(whh, s);
+        const float r[3] = {r4.x, r4.y, r4.z}, f[3] = {f4.x, f4.y, f4.z};
+        float hk[3];
+        half_kick<P>(c, r, f, hk);
+        COL(ww, s) = make_float4(P::add(wh4.x, hk[0]), P::add(wh4.y, hk[1]), P::add(wh4.z, hk[2]), 0.0f);
+      }
+      time = __fadd_rn(time, c.dt);
+      ++steps;
+      inrange_total += in_step;
+    }
+    done_steps = steps - m.steps;
+    for (uint32_t s = 0; s < a; ++s) {
+      heroam_particle *p = base + act[s];
+      const float4 r4 = COL(pos, s), f4 = COL(frc, s), q4 = COL(qq, s), w4 = COL(ww, s), wh4 = COL(whh, s);
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w}, r[3] = {r4.x, r4.y, r4.z}, w[3] = {w4.x, w4.y, w4.z};
+      if (met) {
+        const float wh[3] = {wh4.x, wh4.y, wh4.z}, r_old[3] = {r4.w, f4.w, w4.w};
+        write_midstep<P>(c, p, q, r, w, wh, r_old, time, steps > 0);
+      } else if (done_steps > 0) {
+        const float f[3] = {f4.x, f4.y, f4.z};
+        write_clean<P>(c, p, q, r, w, f, time, act[s] + 1u < m.no);
+      }
+    }
+    if (met) m.status = ST_MIDSTEP;
+    m.steps = steps;
+    m.time = time;
+    v.meta[t] = m;
+  }
+#undef COL
+  if (done_steps) {
+    atomicAdd(&v.counters->particle_steps, done_steps * a);
+    atomicAdd(&v.counters->pair_steps, done_steps * ((unsigned long long)a * (a - 1) / 2));
+    atomicAdd(&v.counters->inrange_steps, inrange_total);
   }
 }
 
@@ -573,8 +847,8 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
       q[i][0] = p->orientation[0]; q[i][1] = p->orientation[1];
       q[i][2] = p->orientation[2]; q[i][3] = p->orientation[3];
       ld3(p->position, r[i]);
-      ld3(p->ang_velocity, w[i]);
-      ld3(p->force, f[i]);
+      load_w<P>(c, p->ang_velocity, w[i]);
+      load_f<P>(c, p->force, f[i]);
       half_kick<P>(c, r[i], f[i], hk[i]);
     } else {
       q[i][0] = 1.0f; q[i][1] = q[i][2] = q[i][3] = 0.0f;
@@ -618,11 +892,10 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
           const uint32_t s = lane + 32u * i;
           const bool valid = own[i] && p < a && s != p;
           g[u][i] = pair_geom<P>(c, r[i], rp);  // own particle first: sign of (r_s - r_p)
-          g[u][i].inside = g[u][i].inside && valid;
-          g[u][i].bin = g[u][i].inside ? g[u][i].bin : 0;
-          tv[u][i] = pair_gather(v.table, g[u][i]);
+          if (!valid) { g[u][i].bin = (unsigned)c.grid_len; g[u][i].inside = false; }  // the zero entry
+          tv[u][i] = pair_gather<P>(v, g[u][i]);
           dmin = fminf(dmin, valid ? g[u][i].d : 3.0e38f);
-          in_step += (g[u][i].inside && s < p) ? 1u : 0u;  // count each pair once
+          if (P::count) in_step += (g[u][i].inside && s < p) ? 1u : 0u;  // count each pair once
         }
       }
 #pragma unroll
@@ -630,7 +903,7 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
           // a masked slot may have d == 0 (the particle itself): keep sqrt away from it
-          const float dsafe = g[u][i].inside ? g[u][i].d : 1.0f;
+          const float dsafe = g[u][i].d > 0.0f ? g[u][i].d : 1.0f;
           pair_apply_own<P>(pair_scale<P>(tv[u][i], dsafe), g[u][i], f[i]);
         }
     }
@@ -655,31 +928,10 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
     if (!own[i]) continue;
     heroam_particle *p = rec[i];
     if (met) {
-      p->orientation[0] = q[i][0]; p->orientation[1] = q[i][1];
-      p->orientation[2] = q[i][2]; p->orientation[3] = q[i][3];
-      st3(p->position, r[i]);
-      st3(p->ang_velocity, w[i]);
-      st3(p->force, wh[i]);
-      p->time = time;
-      if (steps > 0) {
-        float vel[3], v2;
-        stored_velocity<P>(r_old[i], w[i], vel, v2);
-        st3(p->velocity, vel);
-        p->velocity_sq = v2;
-      }
+      write_midstep<P>(c, p, q[i], r[i], w[i], wh[i], r_old[i], time, steps > 0);
     } else if (done_steps > 0) {
-      p->orientation[0] = q[i][0]; p->orientation[1] = q[i][1];
-      p->orientation[2] = q[i][2]; p->orientation[3] = q[i][3];
-      st3(p->position, r[i]);
-      st3(p->ang_velocity, w[i]);
-      st3(p->force, f[i]);
-      float vel[3], v2;
-      stored_velocity<P>(r[i], w[i], vel, v2);
-      st3(p->velocity, vel);
-      p->velocity_sq = v2;
-      p->time = time;
       const uint32_t j = (uint32_t)(p - (v.particles + m.first));
-      p->force_mag = (j + 1u < m.no) ? vec_norm(f[i]) : 0.0f;
+      write_clean<P>(c, p, q[i], r[i], w[i], f[i], time, j + 1u < m.no);
     }
   }
   const unsigned long long ir = warp_sum_u64(inrange_total);
@@ -788,6 +1040,12 @@ __global__ void k_results(DevView v, heroam_traj_result *__restrict__ out) {
   r.n_flagged = m.n_flagged;
   r.time = m.time;
   out[t] = r;
+}
+
+// the Turbo kernels' table: every entry times kappa (the appended zero stays zero)
+__global__ void k_scale_table(float *__restrict__ dst, const float *__restrict__ src, unsigned n, float kappa) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * kappa;
 }
 
 // ---------------------------------------------------------------------------------

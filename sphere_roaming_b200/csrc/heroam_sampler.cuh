@@ -461,9 +461,13 @@ static uint32_t pool_slot_capacity(double lambda) {
   return cap;
 }
 
-template <class P>
+template <class R, class H>
 static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, uint32_t slots) {
   DevView v = make_view(ctx, c);
+  if (H::turbo) {
+    int rc = refresh_scaled_table(ctx, c);
+    if (rc) return rc;
+  }
   const unsigned tgrid = (slots + 127) / 128;
   const uint32_t step_cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu
                                                                                          : (uint32_t)ctx->opt.max_steps;
@@ -479,7 +483,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
     Segments sg = make_segments(ctx->opt.segment_steps);
     sg.free_stride = ctx->free_stride;
     sg.drain = draining ? 1u : 0u;
-    k_pool_resolve<P><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
+    k_pool_resolve<R><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
                                                      ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
@@ -516,7 +520,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
       const uint32_t cnt = ctx->h_bin_count[b];
       if (!cnt) continue;
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<P>(ctx, v, b, cnt);
+      int rc = launch_bin<H>(ctx, v, b, cnt);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
@@ -571,7 +575,10 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
   CU(cudaMemsetAsync(d_stats, 0, sizeof(DevStats), ctx->main));
   CU(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->main));
   CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
-  rc = ctx->opt.mode == HEROAM_MODE_EXACT ? run_pool<Exact>(ctx, c, pool, slots) : run_pool<Fast>(ctx, c, pool, slots);
+  rc = ctx->opt.mode == HEROAM_MODE_EXACT        ? run_pool<Exact, Exact>(ctx, c, pool, slots)
+       : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN ? run_pool<Fast, Fast>(ctx, c, pool, slots)
+       : ctx->opt.count_work                     ? run_pool<Fast, TurboCount>(ctx, c, pool, slots)
+                                                 : run_pool<Fast, Turbo>(ctx, c, pool, slots);
   DevStats *h = (DevStats *)malloc(sizeof(DevStats));
   if (rc == HEROAM_OK) {
     if (cudaMemcpyAsync(h, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||

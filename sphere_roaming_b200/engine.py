@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_HERE, "libheroam_gpu.so")
 
 MODE_EXACT = 0
 MODE_FAST = 1
-_MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, 0: MODE_EXACT, 1: MODE_FAST}
+MODE_FAST_PLAIN = 2
+_MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, "fast_plain": MODE_FAST_PLAIN, 0: MODE_EXACT, 1: MODE_FAST, 2: MODE_FAST_PLAIN}
 
 DONE_SUCCESS, DONE_MAXTIME, DONE_DEADLOCK, DONE_STEPCAP, DONE_UNSUPPORTED = 0, 1, 2, 4, 6
 
@@ -60,7 +61,8 @@ class Options(C.Structure):
         ("max_steps", C.c_ulonglong),
         ("wide_kernel", C.c_int),
         ("pool_slots", C.c_uint),
-        ("reserved", C.c_int * 2),
+        ("count_work", C.c_int),
+        ("reserved", C.c_int * 1),
     ]
 
 
@@ -159,7 +161,7 @@ class Engine:
     """One GPU context (``heroam_gpu_create``): force table resident on the device."""
 
     def __init__(self, conf: Config, table: np.ndarray, device: int = 0, mode="exact", segment_steps: int = 0,
-                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0):
+                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0):
         self.lib = load_library()
         self.conf = conf
         table = np.ascontiguousarray(table, dtype=np.float32)
@@ -171,6 +173,7 @@ class Engine:
         opt.max_steps = max_steps
         opt.wide_kernel = wide_kernel
         opt.pool_slots = pool_slots
+        opt.count_work = count_work
         h = C.c_void_p()
         self._check(self.lib.heroam_gpu_create(C.byref(conf), table.ctypes.data_as(C.POINTER(C.c_float)), device,
                                                C.byref(opt), C.byref(h)))

@@ -82,10 +82,12 @@ def test_wide_kernels_match_oracle(need_gpu, port, table, intensity, max_time):
     counts, init = port.sample(conf, he, table, n, source="philox")
     assert counts.max() <= 128 and counts.max() > (64 if intensity > 2 else 32)
     want, wres = port.simulate(conf, he, table, counts, init)
-    with engine.Engine(conf, table, mode="exact", segment_steps=500) as eng:
-        got, res = eng.simulate(he, counts, init)
-    assert_records_equal(got, want, "warp kernels")
-    assert np.array_equal(res["steps"], wres["steps"]) and np.array_equal(res["n_flagged"], wres["n_flagged"])
+    # 0: hybrid (9..12) + shared-memory (13..16) + warp kernels; 2: warp kernels for all > 8; 3: shared-memory for 9..16
+    for wide in (0, 2, 3):
+        with engine.Engine(conf, table, mode="exact", segment_steps=500, wide_kernel=wide) as eng:
+            got, res = eng.simulate(he, counts, init)
+        assert_records_equal(got, want, f"wide kernels (wide_kernel={wide})")
+        assert np.array_equal(res["steps"], wres["steps"]) and np.array_equal(res["n_flagged"], wres["n_flagged"])
     short = make_config(number=n, max_time=200.0, intensity=intensity, helium_number=he)
     want_s, _ = port.simulate(short, he, table, counts, init)
     with engine.Engine(short, table, mode="exact", wide_kernel=1) as eng:
