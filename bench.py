@@ -309,6 +309,15 @@ def gpu_arm(args, table):
     e2e_s = max_over_ranks(e2e_s)
     e2e_total_ps = sum_over_ranks(e2e_ps)
 
+    # ---- in-range share of the evaluated pairs (the fast kernels do not count it while timed) ----
+    with engine.Engine(conf, table, device=local, mode=args.mode, segment_steps=args.segment, count_work=1) as eng_c:
+        ci = eng_c.run_stats(HE, min(B, 32768), first_index=block(30000, 1)[0])["info"]
+    inrange_ratio = ci["inrange_steps"] / max(1, ci["pair_steps"] - ci["pair_skipped"])
+    if work["inrange_steps"] < 0.5 * inrange_ratio * (work["pair_steps"] - work["pair_skipped"]):
+        work["inrange_steps"] = int(inrange_ratio * (work["pair_steps"] - work["pair_skipped"]))
+        tot_flops = sum_over_ranks(executed_flop_model(work))
+        tot_flops_ref = sum_over_ranks(flop_model(work))
+
     # ---- exact mode, one batch, for the record ----------------------------------------------
     exact = None
     if args.mode != "exact" and args.exact_step:
@@ -343,6 +352,7 @@ def gpu_arm(args, table):
                          "frac": achieved / (peak_tflops * world), "traffic": traffic,
                          "frac_of_reference_work": tot_flops_ref / integ_s / 1e12 / (peak_tflops * world),
                          "free_flight_share_of_particle_steps": tot_free / tot_ps,
+                         "inrange_share_of_evaluated_pairs": inrange_ratio,
                          "model": "flops actually evaluated: 100 per full particle-step, 41 per free-flight particle-step, 10 per "
                                   "evaluated pair-step, +14 per in-range pair-step, over the CUDA-event time of the integrate "
                                   "kernels (frac_of_reference_work charges the SURVEY.md 8d model 100/10/14 for every step and "

@@ -387,9 +387,8 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   ctx->info.kernel_launches++;
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
-    Segments sg = make_segments(ctx->opt.segment_steps);
+    Segments sg = make_segments(ctx->opt.segment_steps, draining);
     sg.free_stride = ctx->free_stride;
-    sg.drain = draining ? 1u : 0u;
     k_resolve_and_bin<R><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
@@ -408,7 +407,8 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
       uint64_t trajectories = 0, flying = 0;
       for (int b = 1; b < BIN_FREE; ++b) trajectories += ctx->h_bin_count[b];
       for (int b = BIN_FREE; b < N_BINS; ++b) flying += ctx->h_bin_count[b];
-      draining = trajectories + flying / 2 < (uint64_t)ctx->sm_count * 256;
+      // fewer trajectories in the full kernels than fill the GPU once: latency-bound from here on
+      draining = trajectories < (uint64_t)ctx->sm_count * 768;
     }
     ctx->info.passes++;
     CU(cudaEventRecord(ctx->ev_i0, ctx->main));

@@ -266,20 +266,37 @@ struct Segments {
                           // the short free-flight tier would only slow per-pass progress
 };
 
-__host__ inline Segments make_segments(uint32_t base) {
+__host__ inline Segments make_segments(uint32_t base, bool drain) {
   Segments sg;
   auto scaled = [base](uint32_t num, uint32_t den) { uint32_t v = (uint32_t)((unsigned long long)base * num / den); return v ? v : 1u; };
   sg.of_bin[0] = base;
-  sg.of_bin[1] = sg.of_bin[2] = scaled(2, 1);
-  sg.of_bin[3] = sg.of_bin[4] = base;
-  sg.of_bin[5] = sg.of_bin[6] = scaled(1, 2);
-  sg.of_bin[7] = sg.of_bin[8] = scaled(1, 4);
-  for (int b = THREAD_MAX_A + 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(1, 8);
-  sg.of_bin[BIN_SMEM16] = scaled(1, 8);
-  sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
+  if (!drain) {
+    // throughput-bound regime (the GPU is full): pass time is the sum of the kernels' work
+    sg.of_bin[1] = sg.of_bin[2] = scaled(2, 1);
+    sg.of_bin[3] = sg.of_bin[4] = base;
+    sg.of_bin[5] = sg.of_bin[6] = scaled(1, 2);
+    sg.of_bin[7] = sg.of_bin[8] = scaled(1, 4);
+    for (int b = THREAD_MAX_A + 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(1, 8);
+    sg.of_bin[BIN_SMEM16] = scaled(1, 8);
+    sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
+  } else {
+    // latency-bound regime (less than a wave of threads): every kernel lasts segment x
+    // chain latency of one step and the pass lasts as long as the slowest, so give each bin
+    // about the same wall time (~0.3 us per step at 2 particles, growing with the pair count)
+    sg.of_bin[1] = sg.of_bin[2] = sg.of_bin[3] = scaled(2, 1);
+    sg.of_bin[4] = scaled(3, 2);
+    sg.of_bin[5] = sg.of_bin[6] = base;
+    sg.of_bin[7] = sg.of_bin[8] = scaled(1, 2);
+    for (int b = THREAD_MAX_A + 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(1, 4);
+    sg.of_bin[BIN_SMEM16] = scaled(1, 8);
+    sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
+  }
+  // free flight: ~73 ns per step; the short tier is dropped while draining (schedule_segment)
   sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
   sg.of_bin[BIN_FREE + 1] = scaled(2, 1);
-  sg.of_bin[BIN_FREE + 2] = scaled(16, 1);
+  sg.of_bin[BIN_FREE + 2] = scaled(8, 1);
+  sg.free_stride = 0;
+  sg.drain = drain ? 1u : 0u;
   return sg;
 }
 

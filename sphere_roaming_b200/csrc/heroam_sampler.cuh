@@ -480,9 +480,8 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
   ctx->info.kernel_launches++;
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
-    Segments sg = make_segments(ctx->opt.segment_steps);
+    Segments sg = make_segments(ctx->opt.segment_steps, draining);
     sg.free_stride = ctx->free_stride;
-    sg.drain = draining ? 1u : 0u;
     k_pool_resolve<R><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
                                                      ctx->d_free_list);
     CU(cudaGetLastError());
@@ -508,7 +507,8 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
       for (int b = 1; b < BIN_FREE; ++b) trajectories += ctx->h_bin_count[b];
       uint64_t flying = 0;
       for (int b = BIN_FREE; b < N_BINS; ++b) flying += ctx->h_bin_count[b];
-      draining = trajectories + flying / 2 < (uint64_t)ctx->sm_count * 256;
+      // fewer trajectories in the full kernels than fill the GPU once: latency-bound from here on
+      draining = trajectories < (uint64_t)ctx->sm_count * 768;
     }
     ctx->info.passes++;
     if (trace) {
