@@ -69,6 +69,9 @@ struct Consts {
   float inv_kappa;
   float inv_half_dt;
   float pos_bias;    // -grid_start * inv_grid
+  // rigorous reach bounds (partner lists)
+  float f_max;       // max |table| over squared distances >= icd^2 (unmet pairs are never closer)
+  float inv_mr;      // 1 / (mass * radius): |angular acceleration| <= |F| * inv_mr
 };
 
 struct Counters {     // roofline work counters
@@ -80,6 +83,8 @@ struct Counters {     // roofline work counters
   unsigned long long free_steps;    // particle-steps taken in free flight (orientation update only)
 };
 
+constexpr uint32_t NBR_ALL = 0xffffffffu;
+
 struct DevView {       // everything a kernel needs, passed by value
   Consts c;
   const float *__restrict__ table;    // grid_len + 1 entries, the last one 0 (out-of-table bin)
@@ -87,6 +92,12 @@ struct DevView {       // everything a kernel needs, passed by value
   heroam_particle *particles;
   TrajMeta *meta;
   uint32_t *act;       // act[first + s] = index (within the trajectory) of its s-th active particle
+  // partner lists of the warp-per-trajectory kernels (rebuilt every pass by the resolve kernel)
+  uint8_t *nbr_pool;   // concatenated ascending partner slots
+  uint32_t *nbr_start; // [first + s] offset of slot s's partners in nbr_pool
+  uint32_t *nbr_cnt;   // [first + s] number of partners; NBR_ALL = iterate over every other particle
+  unsigned long long *nbr_used;
+  unsigned long long nbr_cap;
   Counters *counters;
   uint32_t n_traj;
 };

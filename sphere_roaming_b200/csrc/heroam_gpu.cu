@@ -53,6 +53,11 @@ struct heroam_ctx {
   size_t cap_particles = 0;
   TrajMeta *d_meta = nullptr;
   uint32_t *d_act = nullptr, *d_first = nullptr, *d_counts = nullptr, *d_bin_list = nullptr;
+  uint8_t *d_nbr_pool = nullptr;       // partner lists of the warp kernels
+  uint32_t *d_nbr_start = nullptr, *d_nbr_cnt = nullptr;
+  unsigned long long *d_nbr_used = nullptr;
+  unsigned long long nbr_cap = 0;
+  float f_max = 0.0f;
   uint2 *d_free_list = nullptr;  // (trajectory, active slot) per particle in free flight, N_FREE_TIERS lists
   uint32_t free_stride = 0;      // entries per tier
   heroam_traj_result *d_results = nullptr;
@@ -125,6 +130,7 @@ static int make_consts(const heroam_config &conf, unsigned long long he_number, 
   c.inv_kappa = 1.0f / c.kappa;
   c.inv_half_dt = 1.0f / c.half_dt;
   c.pos_bias = -c.grid_start * c.inv_grid;
+  c.inv_mr = (float)(1.0 / ((double)conf.mass * (double)c.radius));
   c.radius2 = 2.0f * c.radius;
   *out = c;
   return HEROAM_OK;
@@ -173,6 +179,17 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   CU(cudaMalloc(&ctx->d_table_k, ((size_t)ctx->table_len + 1) * sizeof(float)));
   CU(cudaMemset(ctx->d_table, 0, ((size_t)ctx->table_len + 1) * sizeof(float)));
   CU(cudaMemcpy(ctx->d_table, force_list, (size_t)ctx->table_len * sizeof(float), cudaMemcpyHostToDevice));
+  {  // largest force magnitude a pair that has not met can feel (squared distance >= icd^2)
+    const double icd2 = (double)conf->icd_dist * (double)conf->icd_dist;
+    long i0 = (long)floor((icd2 - (double)conf->force_grid_start) / (double)conf->force_grid) - 1;
+    if (i0 < 0) i0 = 0;
+    float fm = 0.0f;
+    for (long i = i0; i < ctx->table_len; ++i) fm = fmaxf(fm, fabsf(force_list[i]));
+    ctx->f_max = fm;
+  }
+  ctx->nbr_cap = 64ull << 20;
+  CU(cudaMalloc(&ctx->d_nbr_pool, ctx->nbr_cap));
+  CU(cudaMalloc(&ctx->d_nbr_used, sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_bin_count, N_BINS * sizeof(uint32_t)));
   CU(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
   CU(cudaMallocHost(&ctx->h_bin_count, N_BINS * sizeof(uint32_t)));
@@ -187,6 +204,10 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
   cudaDeviceSynchronize();
   cudaFree(ctx->d_table);
   cudaFree(ctx->d_table_k);
+  cudaFree(ctx->d_nbr_pool);
+  cudaFree(ctx->d_nbr_start);
+  cudaFree(ctx->d_nbr_cnt);
+  cudaFree(ctx->d_nbr_used);
   cudaFree(ctx->d_particles);
   cudaFree(ctx->d_meta);
   cudaFree(ctx->d_act);
@@ -226,8 +247,13 @@ static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
     ctx->d_particles = nullptr;
     ctx->d_act = nullptr;
     ctx->cap_particles = 0;
+    cudaFree(ctx->d_nbr_start);
+    cudaFree(ctx->d_nbr_cnt);
+    ctx->d_nbr_start = ctx->d_nbr_cnt = nullptr;
     CU(cudaMalloc(&ctx->d_particles, n_particles * sizeof(heroam_particle)));
     CU(cudaMalloc(&ctx->d_act, n_particles * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_nbr_start, n_particles * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_nbr_cnt, n_particles * sizeof(uint32_t)));
     ctx->cap_particles = n_particles;
   }
   if (n_traj > ctx->cap_traj) {
@@ -258,11 +284,17 @@ static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
 static DevView make_view(heroam_ctx *ctx, const Consts &c) {
   DevView v;
   v.c = c;
+  v.c.f_max = ctx->f_max;
   v.table = ctx->d_table;
   v.table_k = ctx->d_table_k;
   v.particles = ctx->d_particles;
   v.meta = ctx->d_meta;
   v.act = ctx->d_act;
+  v.nbr_pool = ctx->d_nbr_pool;
+  v.nbr_start = ctx->d_nbr_start;
+  v.nbr_cnt = ctx->d_nbr_cnt;
+  v.nbr_used = ctx->d_nbr_used;
+  v.nbr_cap = ctx->nbr_cap;
   v.counters = ctx->d_counters;
   v.n_traj = ctx->n_traj;
   return v;
@@ -352,11 +384,12 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) 
         CU(cudaFuncSetAttribute(k_integrate_smem<16, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         k_integrate_smem<16, P><<<sgrid, SMEM_TPB, bytes, s>>>(v, list, cnt);
       } else if (bin <= BIN_WARP1) {
-        k_integrate_warp<1, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+        // partner lists exist for the warp bins proper (schedule_segment), not for narrower bins
+        k_integrate_warp<1, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt, bin == BIN_WARP1);
       } else if (bin == BIN_WARP2) {
-        k_integrate_warp<2, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+        k_integrate_warp<2, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt, true);
       } else {
-        k_integrate_warp<4, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt);
+        k_integrate_warp<4, P><<<wgrid, 32 * WARP_KERNEL_WARPS, 0, s>>>(v, list, cnt, true);
       }
       break;
     }
@@ -387,6 +420,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   ctx->info.kernel_launches++;
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
+    CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     Segments sg = make_segments(ctx->opt.segment_steps, draining);
     sg.free_stride = ctx->free_stride;
     k_resolve_and_bin<R><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);

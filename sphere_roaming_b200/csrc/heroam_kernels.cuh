@@ -337,6 +337,65 @@ __device__ inline uint32_t free_flight_horizon(const DevView &v, const TrajMeta 
   return horizon < 1.0 ? 0u : (horizon > 4.0e9 ? 0xffffffffu : (uint32_t)horizon);
 }
 
+// Partner lists for the warp-per-trajectory kernels.  Slot s's list holds, in ascending
+// order, every other moving particle that could come within D_far of it during the next
+// `window` steps; all other pairs are provably force-free and cannot meet for that long, so
+// skipping them leaves every value as it is (they would add exact zeros).  Reach of a
+// particle over the window: it starts at |w| and can gain at most dt * (linked partners) *
+// f_max / (m R) of angular speed per step (|torque| <= R |F|), so it travels at most
+//     R dt (|w| W + dt deg f_max / (m R) W^2 / 2).
+// deg itself comes out of the linking: iterate to the (monotone) fixed point.
+__device__ inline void build_partner_lists(const DevView &v, const TrajMeta &m, uint32_t window) {
+  const uint32_t a = m.n_active;
+  const heroam_particle *base = v.particles + m.first;
+  const uint32_t *act = v.act + m.first;
+  float w0[MAX_ACTIVE];
+  uint8_t deg[MAX_ACTIVE];
+  const double R = (double)v.c.radius, dt = (double)v.c.dt, W = (double)window;
+  const double d_far = sqrt((double)v.c.far2);
+  const double gain = dt * (double)v.c.f_max * (double)v.c.inv_mr * 1.01;  // angular speed per step per partner
+  for (uint32_t s = 0; s < a; ++s) {
+    const float *w = base[act[s]].ang_velocity;
+    w0[s] = (float)(sqrt((double)w[0] * w[0] + (double)w[1] * w[1] + (double)w[2] * w[2]) * 1.01);
+    deg[s] = 0;
+  }
+  auto reach = [&](uint32_t s) { return R * dt * ((double)w0[s] * W + 0.5 * gain * (double)deg[s] * W * W) + 2.0e-6 * R * W + 1.0e-3; };
+  auto dist = [&](uint32_t j, uint32_t k) {
+    const float *pj = base[act[j]].position, *pk = base[act[k]].position;
+    const double dx = (double)pj[0] - pk[0], dy = (double)pj[1] - pk[1], dz = (double)pj[2] - pk[2];
+    return sqrt(dx * dx + dy * dy + dz * dz);
+  };
+  for (int iter = 0; iter < 16; ++iter) {
+    bool grew = false;
+    for (uint32_t j = 0; j < a; ++j) {
+      uint32_t n = 0;
+      const double rj = reach(j);
+      for (uint32_t k = 0; k < a; ++k)
+        if (k != j && dist(j, k) - d_far <= rj + reach(k)) ++n;
+      if (n > deg[j]) { deg[j] = (uint8_t)n; grew = true; }
+    }
+    if (!grew) break;
+    if (iter == 15) for (uint32_t s = 0; s < a; ++s) deg[s] = (uint8_t)(a - 1);  // no fixed point in time: link all
+  }
+  unsigned long long total = 0;
+  for (uint32_t s = 0; s < a; ++s) total += deg[s];
+  const unsigned long long at = atomicAdd(v.nbr_used, total);
+  if (at + total > v.nbr_cap) {  // pool exhausted: this trajectory iterates over all partners
+    for (uint32_t s = 0; s < a; ++s) v.nbr_cnt[m.first + s] = NBR_ALL;
+    return;
+  }
+  unsigned long long cursor = at;
+  for (uint32_t j = 0; j < a; ++j) {
+    v.nbr_start[m.first + j] = (uint32_t)cursor;
+    uint32_t n = 0;
+    const double rj = reach(j);
+    for (uint32_t k = 0; k < a && n < deg[j]; ++k)
+      if (k != j && dist(j, k) - d_far <= rj + reach(k)) v.nbr_pool[cursor + n++] = (uint8_t)k;
+    v.nbr_cnt[m.first + j] = n;
+    cursor += deg[j];
+  }
+}
+
 // List the active particles, choose the bin, and fix the step at which the segment ends.
 __device__ inline int schedule_segment(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap) {
   uint32_t s = 0;
@@ -360,6 +419,7 @@ __device__ inline int schedule_segment(const DevView &v, TrajMeta &m, const Segm
   if (stop > step_cap) stop = step_cap;
   m.step_stop = stop;
   if (bin >= BIN_FREE) m.status = ST_FLYING;
+  if (bin >= BIN_WARP1 && bin <= BIN_WARP4 && stop > m.steps) build_partner_lists(v, m, stop - m.steps);
   return bin;
 }
 
@@ -841,7 +901,7 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_smem(DevView v, const ui
 // ---------------------------------------------------------------------------------
 template <int PPL, class P>
 __global__ void __launch_bounds__(32 * WARP_KERNEL_WARPS)
-k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
+k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count, bool use_lists) {
   __shared__ float4 s_pos[WARP_KERNEL_WARPS][32 * PPL];
   const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   const uint32_t item = blockIdx.x * WARP_KERNEL_WARPS + wib;
@@ -873,6 +933,25 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
       for (int d = 0; d < 3; ++d) { r[i][d] = 0.0f; w[i][d] = 0.0f; f[i][d] = 0.0f; hk[i][d] = 0.0f; }
     }
   }
+  // partner lists built by the resolve kernel for exactly this segment
+  const uint8_t *nbr[PPL];
+  uint32_t n_nbr[PPL];
+  uint32_t my_len = 0, my_pairs = 0;
+  bool listed_lane = true;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const uint32_t s = lane + 32u * i;
+    n_nbr[i] = !use_lists ? NBR_ALL : (own[i] ? v.nbr_cnt[m.first + s] : 0u);
+    nbr[i] = v.nbr_pool + ((use_lists && own[i]) ? v.nbr_start[m.first + s] : 0u);
+    if (n_nbr[i] == NBR_ALL) { listed_lane = false; n_nbr[i] = 0; }
+    my_len = max(my_len, n_nbr[i]);
+    my_pairs += n_nbr[i];
+  }
+  const bool listed = __all_sync(0xffffffffu, listed_lane);
+  const uint32_t loop_len = listed ? __reduce_max_sync(0xffffffffu, my_len) : a;
+  // pairs evaluated per step (each listed pair sits in two lists)
+  const unsigned long long evaluated = listed ? __reduce_add_sync(0xffffffffu, my_pairs) / 2u
+                                              : (unsigned long long)a * (a - 1) / 2;
   uint32_t steps = m.steps;
   float time = m.time;
   bool met = false;
@@ -894,20 +973,30 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
     float dmin = 3.0e38f;
     uint32_t in_step = 0;
     // partners in ascending order, four at a time: geometry and gathers first, then the
-    // (ordered) accumulation; everything branch-free, invalid slots contribute zero
+    // (ordered) accumulation; everything branch-free, invalid slots contribute zero.
+    // With partner lists (the usual case) slot k of the loop is the k-th listed partner of
+    // each lane's particle; without, it is particle k itself.
     constexpr int UNR = 4;
-    for (uint32_t p0 = 0; p0 < a; p0 += UNR) {
+    for (uint32_t p0 = 0; p0 < loop_len; p0 += UNR) {
       PairGeom g[UNR][PPL];
       float tv[UNR][PPL];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        const uint32_t p = p0 + u;
-        const float4 rp4 = pos[p < a ? p : a - 1u];
-        const float rp[3] = {rp4.x, rp4.y, rp4.z};
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
           const uint32_t s = lane + 32u * i;
-          const bool valid = own[i] && p < a && s != p;
+          const uint32_t k = p0 + u;
+          uint32_t p = k;
+          bool valid = own[i];
+          if (listed) {
+            valid = valid && k < n_nbr[i];
+            p = valid ? (uint32_t)nbr[i][k] : s;
+          } else {
+            valid = valid && k < a && s != k;
+            p = k < a ? k : a - 1u;
+          }
+          const float4 rp4 = pos[own[i] ? p : 0u];
+          const float rp[3] = {rp4.x, rp4.y, rp4.z};
           g[u][i] = pair_geom<P>(c, r[i], rp);  // own particle first: sign of (r_s - r_p)
           if (!valid) { g[u][i].bin = (unsigned)c.grid_len; g[u][i].inside = false; }  // the zero entry
           tv[u][i] = pair_gather<P>(v, g[u][i]);
@@ -960,6 +1049,7 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
     if (done_steps) {
       atomicAdd(&v.counters->particle_steps, done_steps * a);
       atomicAdd(&v.counters->pair_steps, done_steps * ((unsigned long long)a * (a - 1) / 2));
+      atomicAdd(&v.counters->pair_skipped, done_steps * ((unsigned long long)a * (a - 1) / 2 - evaluated));
       atomicAdd(&v.counters->inrange_steps, ir);
     }
   }

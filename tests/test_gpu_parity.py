@@ -95,6 +95,24 @@ def test_wide_kernels_match_oracle(need_gpu, port, table, intensity, max_time):
     assert_records_equal(got_s, want_s, "record-resident kernel")
 
 
+def test_sparse_large_droplet_partner_lists(need_gpu, port, table):
+    """Config C3's regime proper: N_He = 1e7 (R = 478 A), ~49 excitations, almost every pair out of
+    range.  The warp kernels then work from partner lists (pairs that provably cannot interact during
+    the segment are skipped); results must still be bit-identical to the oracle, which evaluates all."""
+    n, he, max_time = 24, 10**7, 6000.0
+    conf = make_config(number=n, max_time=max_time, intensity=0.0125, helium_number=he)
+    counts, init = port.sample(conf, he, table, n, source="philox")
+    assert 30 < counts.mean() < 70
+    want, wres, wctr = port.simulate(conf, he, table, counts, init, want_counters=True)
+    with engine.Engine(conf, table, mode="exact", segment_steps=4096) as eng:
+        got, res = eng.simulate(he, counts, init)
+        info = eng.run_info()
+    assert_records_equal(got, want, "sparse large droplet")
+    assert np.array_equal(res["steps"], wres["steps"])
+    assert info["pair_steps"] == wctr["pair_steps"] and info["inrange_steps"] == wctr["inrange_steps"]
+    assert info["pair_skipped"] > 0.9 * info["pair_steps"], "the partner lists should skip almost every pair here"
+
+
 def test_fast_mode_within_stated_tolerance(need_gpu, port, table):
     n, max_time = 4096, 2.0e5
     conf = make_config(number=n, max_time=max_time)
