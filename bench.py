@@ -49,8 +49,8 @@ def workload_config(args):
     return {
         "workload": "C2: repo config.conf physics (N_He=1e4, I=1 GW/cm2, tau=100 fs, lambda=3.93), "
                     "T-ref synthetic force table 1596000 x f32 on r^2, dt=1 fs, max_time=%g fs, "
-                    "seed 100401452; one step = one batch of trajectories of the 1e6-trajectory run, the K "
-                    "steps streamed through the engine back to back" % args.max_time,
+                    "seed 100401452; one step = one run of `batch_per_gpu` trajectories per GPU (1e6 = the C2 run), "
+                    "the K steps streamed back to back through the engine's retire-and-refill pool" % args.max_time,
         "batch_per_gpu": args.batch,
         "max_time": args.max_time,
         "mode": args.mode,
@@ -323,9 +323,9 @@ def gpu_arm(args, table):
     if args.mode != "exact" and args.exact_step:
         eng.set_mode("exact")
         eng.run_stats(HE, min(B, 8192), first_index=block(20000, 1)[0])
-        st = eng.run_stats(HE, min(B, 65536), first_index=block(W, 1)[0])
+        st = eng.run_stats(HE, min(B, 262144), first_index=block(W, 1)[0])
         exact = {"value": sum_over_ranks(float(st["info"]["particle_steps"])) / max_over_ranks(st["info"]["device_ms"] * 1e-3),
-                 "unit": UNIT, "note": "HEROAM_MODE_EXACT (bit-exact with the strict reference), one run of min(batch, 65536) trajectories (tail dominated)"}
+                 "unit": UNIT, "note": "HEROAM_MODE_EXACT (bit-exact with the strict reference), one run of min(batch, 262144) trajectories (drain dominated)"}
         eng.set_mode(args.mode)
 
     if rank == 0:
@@ -382,11 +382,11 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=262144, help="trajectories per GPU per step")
+    ap.add_argument("--batch", type=int, default=1000000, help="trajectories per GPU per step (C2: 1e6)")
     ap.add_argument("--max-time", type=float, default=1.0e7)
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--segment", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--warmup-e2e", type=int, default=1)
     ap.add_argument("--exact-step", type=int, default=1)
     ap.add_argument("--ref-sample", type=int, default=0)
