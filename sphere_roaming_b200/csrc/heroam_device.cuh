@@ -37,15 +37,23 @@ enum : uint32_t {
   ST_DONE = 16     // ST_DONE + HEROAM_DONE_* once finished
 };
 
-struct TrajMeta {      // 32 bytes per trajectory
+struct TrajMeta {      // 56 bytes per trajectory
   uint32_t first;      // first record of this trajectory in the flat particle array
   uint32_t no;         // particles in the trajectory
-  uint32_t steps;      // completed iterations of the step loop
+  uint32_t steps;      // completed iterations of the step loop (of the core, see below)
   float time;          // the loop's `time` variable (simulation.c:467, :512-517)
   uint32_t n_flagged;  // particles with success == 1
-  uint32_t n_active;   // particles still moving
+  uint32_t n_active;   // particles still moving that the integrate kernels work on (the "core")
   uint32_t status;     // ST_*
   uint32_t step_stop;  // the integrate kernel pauses when steps reaches this
+  // Loners: moving particles that provably cannot come within reach of any other particle
+  // before loner_until.  They fly on their own (k_free_flight) and may be ahead of the core.
+  uint32_t n_loners;
+  uint32_t loner_from;   // step at which their current flight started
+  uint32_t loner_until;  // step they have reached; the core catches up before the next analysis
+  float loner_time0;     // the clock at loner_from
+  uint32_t cross_from;   // core step up to which core-loner / loner-loner pair-steps are accounted
+  uint32_t core_slots;   // act[first .. first+core_slots) = core, then n_loners loner entries
 };
 
 // Loop-invariant scalars, rounded on the host exactly where the reference rounds them.
@@ -92,6 +100,7 @@ struct DevView {       // everything a kernel needs, passed by value
   heroam_particle *particles;
   TrajMeta *meta;
   uint32_t *act;       // act[first + s] = index (within the trajectory) of its s-th active particle
+  float4 *ckpt_q;      // [first + j] orientation of particle j when it last took off as a loner
   // partner lists of the warp-per-trajectory kernels (rebuilt every pass by the resolve kernel)
   uint8_t *nbr_pool;   // concatenated ascending partner slots
   uint32_t *nbr_start; // [first + s] offset of slot s's partners in nbr_pool

@@ -60,6 +60,7 @@ struct heroam_ctx {
   float f_max = 0.0f;
   uint2 *d_free_list = nullptr;  // (trajectory, active slot) per particle in free flight, N_FREE_TIERS lists
   uint32_t free_stride = 0;      // entries per tier
+  float4 *d_ckpt_q = nullptr;    // take-off orientation of loners
   heroam_traj_result *d_results = nullptr;
   size_t cap_traj = 0;
   uint32_t *d_bin_count = nullptr;
@@ -212,6 +213,7 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
   cudaFree(ctx->d_meta);
   cudaFree(ctx->d_act);
   cudaFree(ctx->d_free_list);
+  cudaFree(ctx->d_ckpt_q);
   cudaFree(ctx->d_first);
   cudaFree(ctx->d_counts);
   cudaFree(ctx->d_bin_list);
@@ -249,17 +251,23 @@ static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
     ctx->cap_particles = 0;
     cudaFree(ctx->d_nbr_start);
     cudaFree(ctx->d_nbr_cnt);
+    cudaFree(ctx->d_ckpt_q);
+    cudaFree(ctx->d_free_list);
     ctx->d_nbr_start = ctx->d_nbr_cnt = nullptr;
+    ctx->d_ckpt_q = nullptr;
+    ctx->d_free_list = nullptr;
     CU(cudaMalloc(&ctx->d_particles, n_particles * sizeof(heroam_particle)));
     CU(cudaMalloc(&ctx->d_act, n_particles * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_nbr_start, n_particles * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_nbr_cnt, n_particles * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_ckpt_q, n_particles * sizeof(float4)));
+    // every moving particle can be in flight at once: one entry each, per tier
+    ctx->free_stride = (uint32_t)(n_particles > 0xffffffffull ? 0xffffffffull : n_particles);
+    CU(cudaMalloc(&ctx->d_free_list, (size_t)N_FREE_TIERS * ctx->free_stride * sizeof(uint2)));
     ctx->cap_particles = n_particles;
   }
   if (n_traj > ctx->cap_traj) {
     cudaFree(ctx->d_meta);
-    cudaFree(ctx->d_free_list);
-    ctx->d_free_list = nullptr;
     cudaFree(ctx->d_first);
     cudaFree(ctx->d_counts);
     cudaFree(ctx->d_bin_list);
@@ -273,9 +281,6 @@ static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
     CU(cudaMalloc(&ctx->d_counts, n_traj * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_bin_list, (size_t)N_BINS * n_traj * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_results, n_traj * sizeof(heroam_traj_result)));
-    // only trajectories with <= FREE_MAX_A moving particles ever fly: FREE_MAX_A entries each suffice
-    ctx->free_stride = (uint32_t)(n_traj * FREE_MAX_A > 0xffffffffull ? 0xffffffffull : n_traj * FREE_MAX_A);
-    CU(cudaMalloc(&ctx->d_free_list, (size_t)N_FREE_TIERS * ctx->free_stride * sizeof(uint2)));
     ctx->cap_traj = n_traj;
   }
   return HEROAM_OK;
@@ -290,6 +295,7 @@ static DevView make_view(heroam_ctx *ctx, const Consts &c) {
   v.particles = ctx->d_particles;
   v.meta = ctx->d_meta;
   v.act = ctx->d_act;
+  v.ckpt_q = ctx->d_ckpt_q;
   v.nbr_pool = ctx->d_nbr_pool;
   v.nbr_start = ctx->d_nbr_start;
   v.nbr_cnt = ctx->d_nbr_cnt;
@@ -350,12 +356,12 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) 
   const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
-  if (bin >= BIN_FREE) {
+  if (bin >= BIN_FREE && bin < BIN_CORE) {
     k_free_flight<P><<<(cnt + 127) / 128, 128, 0, s>>>(v, ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride, cnt);
     CU(cudaGetLastError());
     return HEROAM_OK;
   }
-  switch (bin) {
+  switch (bin >= BIN_CORE ? bin - BIN_CORE : bin) {  // the core of a split trajectory runs in the kernel of its size
     case 1: k_integrate_thread<1, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
     case 2: k_integrate_thread<2, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
     case 3: k_integrate_thread<3, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
@@ -438,9 +444,9 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
     if (live == 0) break;
     {
-      uint64_t trajectories = 0, flying = 0;
-      for (int b = 1; b < BIN_FREE; ++b) trajectories += ctx->h_bin_count[b];
-      for (int b = BIN_FREE; b < N_BINS; ++b) flying += ctx->h_bin_count[b];
+      uint64_t trajectories = 0;
+      for (int b = 1; b < N_BINS; ++b)
+        if (b < BIN_FREE || b >= BIN_CORE) trajectories += ctx->h_bin_count[b];
       // fewer trajectories in the full kernels than fill the GPU once: latency-bound from here on
       draining = trajectories < (uint64_t)ctx->sm_count * 768;
     }

@@ -30,9 +30,11 @@ constexpr int BIN_WARP2 = 15;     // 33..64 active: k_integrate_warp<2> (two par
 constexpr int BIN_WARP4 = 16;     // 65..128 active: k_integrate_warp<4>
 // every pair provably out of reach for a whole segment: k_free_flight, one thread per PARTICLE.
 // Three tiers of FIXED segment length (so that all lanes of a warp run the same trip count):
-constexpr int BIN_FREE = 17;      // BIN_FREE + 0: short, + 1: medium, + 2: long
-constexpr int N_FREE_TIERS = 3;
-constexpr int N_BINS = BIN_FREE + N_FREE_TIERS;
+constexpr int BIN_FREE = 17;      // BIN_FREE + 0: short, + 1: medium, + 2: long (whole trajectory in free flight)
+constexpr int FREE_SPLIT = 3;     // BIN_FREE + 3: loners split off a trajectory whose core keeps interacting
+constexpr int N_FREE_TIERS = 4;
+constexpr int BIN_CORE = BIN_FREE + N_FREE_TIERS;  // BIN_CORE + a: cores of split trajectories, a = 1..8 (k_integrate_thread<a>)
+constexpr int N_BINS = BIN_CORE + 9;
 constexpr int FREE_MAX_A = 8;     // the free-flight analysis is done for trajectories with <= 8 moving particles
 constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
 constexpr int INTEGRATE_TPB = 128;
@@ -133,6 +135,7 @@ __global__ void k_prepare(DevView v, const uint32_t *__restrict__ first,
   m.n_active = m.no - m.n_flagged;
   m.status = ST_LIVE;
   m.step_stop = 0;
+  m.n_loners = 0; m.loner_from = 0; m.loner_until = 0; m.loner_time0 = 0.0f; m.cross_from = 0; m.core_slots = m.n_active;
   v.meta[t] = m;
 }
 
@@ -216,7 +219,7 @@ __device__ void finish_step(const DevView &v, TrajMeta &m, Counters &work) {
   m.n_flagged += a - remaining;
   m.n_active = remaining;
   m.steps += 1;
-  if (remaining > 0) m.time = t_next;  // :512-517, max over particle clocks
+  if (remaining > 0 || m.n_loners > 0) m.time = t_next;  // :512-517, max over particle clocks (loners move too)
   m.status = ST_LIVE;
   work.particle_steps += remaining;
   work.pair_steps += pairs;
@@ -232,13 +235,14 @@ constexpr uint32_t NOT_DONE = 0xffffffffu;
 // The loop condition `!success && time < max_time` (simulation.c:469) plus the defined
 // exits (deadlock, step cap, unsupported width).  Returns a HEROAM_DONE_* code or NOT_DONE.
 __device__ inline uint32_t evaluate_exit(const Consts &c, TrajMeta &m, uint32_t step_cap) {
+  const uint32_t moving = m.n_active + m.n_loners;
   uint32_t done = NOT_DONE;
   if (m.steps == 0) {
     if (!(0.0f < c.max_time)) {
       done = HEROAM_DONE_MAXTIME;  // the reference's loop body never runs
     } else if (step_cap == 0u) {
       done = HEROAM_DONE_STEPCAP;
-    } else if (m.n_active == 0) {
+    } else if (moving == 0) {
       // a step with nobody to move: forces are zeroed at import, no clock advances
       m.steps = 1;
       done = all_paired(m.no, m.n_flagged) ? HEROAM_DONE_SUCCESS : HEROAM_DONE_DEADLOCK;
@@ -247,12 +251,12 @@ __device__ inline uint32_t evaluate_exit(const Consts &c, TrajMeta &m, uint32_t 
     done = HEROAM_DONE_SUCCESS;
   } else if (!(m.time < c.max_time)) {
     done = HEROAM_DONE_MAXTIME;
-  } else if (m.n_active == 0) {
+  } else if (moving == 0) {
     done = HEROAM_DONE_DEADLOCK;
   } else if (m.steps >= step_cap) {
     done = HEROAM_DONE_STEPCAP;
   }
-  if (done == NOT_DONE && m.n_active > (uint32_t)MAX_ACTIVE) done = HEROAM_DONE_UNSUPPORTED;
+  if (done == NOT_DONE && moving > (uint32_t)MAX_ACTIVE) done = HEROAM_DONE_UNSUPPORTED;
   return done;
 }
 
@@ -261,7 +265,7 @@ __device__ inline uint32_t evaluate_exit(const Consts &c, TrajMeta &m, uint32_t 
 // particles per thread) get shorter segments and the cheap free-flight steps longer ones.
 struct Segments {
   uint32_t of_bin[N_BINS];
-  uint32_t free_stride;   // entries reserved per free-flight tier in the free list
+  uint32_t free_stride;   // entries reserved per whole-trajectory free-flight tier in the free list
   uint32_t drain;         // 1 while the run is draining (few live trajectories, latency bound):
                           // the short free-flight tier would only slow per-pass progress
 };
@@ -295,20 +299,81 @@ __host__ inline Segments make_segments(uint32_t base, bool drain) {
   sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
   sg.of_bin[BIN_FREE + 1] = scaled(2, 1);
   sg.of_bin[BIN_FREE + 2] = scaled(8, 1);
+  // split trajectories: core and loners advance by the same fixed window
+  const uint32_t window = drain ? scaled(2, 1) : scaled(1, 2);
+  sg.of_bin[BIN_FREE + FREE_SPLIT] = window;
+  for (int a = 0; a <= THREAD_MAX_A; ++a) sg.of_bin[BIN_CORE + a] = window;
   sg.free_stride = 0;
   sg.drain = drain ? 1u : 0u;
   return sg;
 }
 
-// Free-flight horizon: the number of steps for which NO active pair of the trajectory can
-// come within reach of the force table or of icd_dist, whatever happens.  While that holds
-// every force is exactly zero, angular velocities are constant and the particles are
-// independent.  Bound: a particle with angular velocity w moves its position by at most
-// |w| R dt per step (chord <= arc; rotation angle per step is 2 atan(|w| dt / 2) <= |w| dt),
-// plus rounding of the re-projection (a few ulp of R).  A pair now D apart therefore stays
-// farther than D_far for at least (D - D_far) / (b_j + b_k) steps.  Evaluated in double with
-// 1 % slack on the speeds; forces must be exactly zero on entry (they are whenever the
-// state came out of a step in which every pair was out of range).
+// ---------------------------------------------------------------------------------
+// Reach analysis.  A particle with angular velocity w moves its position by at most |w| R dt
+// per step (chord <= arc; the rotation angle of a step is 2 atan(|w| dt / 2) <= |w| dt) plus
+// rounding of the re-projection (a few ulp of R); under forces its angular speed can grow by
+// at most dt * f_max / (m R) per step and partner within reach (|torque| <= R |F|, and an
+// unmet pair is never closer than icd_dist, so |F| <= f_max).  Over W steps it travels at most
+//     reach = R dt (|w| W + dt deg f_max / (m R) W^2 / 2) + slack,
+// deg = number of partners that could come within D_far of it, which itself follows from the
+// reaches: link(j,k) <=> dist(j,k) - D_far <= reach(j) + reach(k); iterate to the (monotone)
+// fixed point.  Pairs that are not linked are provably out of the table and out of icd_dist
+// for the whole window: they contribute exact zeros and cannot meet.  Evaluated in double
+// with 1 % slack on speeds and forces.
+// ---------------------------------------------------------------------------------
+struct Reach {
+  const heroam_particle *base;
+  const uint32_t *act;
+  uint32_t a;
+  double R, dt, W, d_far, gain;
+  float w0[MAX_ACTIVE];
+  uint8_t deg[MAX_ACTIVE];
+
+  __device__ void init(const DevView &v, const TrajMeta &m, uint32_t count, uint32_t window) {
+    base = v.particles + m.first;
+    act = v.act + m.first;
+    a = count;
+    R = (double)v.c.radius; dt = (double)v.c.dt; W = (double)window;
+    d_far = sqrt((double)v.c.far2);
+    gain = dt * (double)v.c.f_max * (double)v.c.inv_mr * 1.01;
+    for (uint32_t s = 0; s < a; ++s) {
+      const float *w = base[act[s]].ang_velocity;
+      w0[s] = (float)(sqrt((double)w[0] * w[0] + (double)w[1] * w[1] + (double)w[2] * w[2]) * 1.01);
+      deg[s] = 0;
+    }
+  }
+  __device__ double reach(uint32_t s) const {
+    return R * dt * ((double)w0[s] * W + 0.5 * gain * (double)deg[s] * W * W) + 2.0e-6 * R * W + 1.0e-3;
+  }
+  __device__ double dist(uint32_t j, uint32_t k) const {
+    const float *pj = base[act[j]].position, *pk = base[act[k]].position;
+    const double dx = (double)pj[0] - pk[0], dy = (double)pj[1] - pk[1], dz = (double)pj[2] - pk[2];
+    return sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  __device__ bool linked(uint32_t j, uint32_t k) const { return dist(j, k) - d_far <= reach(j) + reach(k); }
+  __device__ void solve() {
+    for (int iter = 0; iter < 16; ++iter) {
+      bool grew = false;
+      for (uint32_t j = 0; j < a; ++j) {
+        uint32_t n = 0;
+        for (uint32_t k = 0; k < a; ++k)
+          if (k != j && linked(j, k)) ++n;
+        if (n > deg[j]) { deg[j] = (uint8_t)n; grew = true; }
+      }
+      if (!grew) return;
+    }
+    for (uint32_t s = 0; s < a; ++s) deg[s] = (uint8_t)(a - 1);  // no fixed point in time: link everything
+  }
+  __device__ bool force_free(uint32_t s) const {
+    const float *f = base[act[s]].force;
+    return f[0] == 0.0f && f[1] == 0.0f && f[2] == 0.0f;
+  }
+};
+
+// Free-flight horizon of a whole trajectory (<= 8 moving particles): the number of steps for
+// which NO pair can come within reach; forces must be exactly zero on entry (they are whenever
+// the state came out of a step in which every pair was out of range).  Without forces the
+// speeds are constant, so the bound is linear: (D - D_far) / (b_j + b_k).
 __device__ inline uint32_t free_flight_horizon(const DevView &v, const TrajMeta &m) {
   const uint32_t a = m.n_active;
   if (a == 0 || a > (uint32_t)FREE_MAX_A) return 0;
@@ -337,48 +402,15 @@ __device__ inline uint32_t free_flight_horizon(const DevView &v, const TrajMeta 
   return horizon < 1.0 ? 0u : (horizon > 4.0e9 ? 0xffffffffu : (uint32_t)horizon);
 }
 
-// Partner lists for the warp-per-trajectory kernels.  Slot s's list holds, in ascending
-// order, every other moving particle that could come within D_far of it during the next
-// `window` steps; all other pairs are provably force-free and cannot meet for that long, so
-// skipping them leaves every value as it is (they would add exact zeros).  Reach of a
-// particle over the window: it starts at |w| and can gain at most dt * (linked partners) *
-// f_max / (m R) of angular speed per step (|torque| <= R |F|), so it travels at most
-//     R dt (|w| W + dt deg f_max / (m R) W^2 / 2).
-// deg itself comes out of the linking: iterate to the (monotone) fixed point.
+// Partner lists for the warp-per-trajectory kernels: slot s's list holds, in ascending order,
+// every other moving particle linked to it for the next `window` steps (see Reach).
 __device__ inline void build_partner_lists(const DevView &v, const TrajMeta &m, uint32_t window) {
+  Reach rc;
+  rc.init(v, m, m.n_active, window);
+  rc.solve();
   const uint32_t a = m.n_active;
-  const heroam_particle *base = v.particles + m.first;
-  const uint32_t *act = v.act + m.first;
-  float w0[MAX_ACTIVE];
-  uint8_t deg[MAX_ACTIVE];
-  const double R = (double)v.c.radius, dt = (double)v.c.dt, W = (double)window;
-  const double d_far = sqrt((double)v.c.far2);
-  const double gain = dt * (double)v.c.f_max * (double)v.c.inv_mr * 1.01;  // angular speed per step per partner
-  for (uint32_t s = 0; s < a; ++s) {
-    const float *w = base[act[s]].ang_velocity;
-    w0[s] = (float)(sqrt((double)w[0] * w[0] + (double)w[1] * w[1] + (double)w[2] * w[2]) * 1.01);
-    deg[s] = 0;
-  }
-  auto reach = [&](uint32_t s) { return R * dt * ((double)w0[s] * W + 0.5 * gain * (double)deg[s] * W * W) + 2.0e-6 * R * W + 1.0e-3; };
-  auto dist = [&](uint32_t j, uint32_t k) {
-    const float *pj = base[act[j]].position, *pk = base[act[k]].position;
-    const double dx = (double)pj[0] - pk[0], dy = (double)pj[1] - pk[1], dz = (double)pj[2] - pk[2];
-    return sqrt(dx * dx + dy * dy + dz * dz);
-  };
-  for (int iter = 0; iter < 16; ++iter) {
-    bool grew = false;
-    for (uint32_t j = 0; j < a; ++j) {
-      uint32_t n = 0;
-      const double rj = reach(j);
-      for (uint32_t k = 0; k < a; ++k)
-        if (k != j && dist(j, k) - d_far <= rj + reach(k)) ++n;
-      if (n > deg[j]) { deg[j] = (uint8_t)n; grew = true; }
-    }
-    if (!grew) break;
-    if (iter == 15) for (uint32_t s = 0; s < a; ++s) deg[s] = (uint8_t)(a - 1);  // no fixed point in time: link all
-  }
   unsigned long long total = 0;
-  for (uint32_t s = 0; s < a; ++s) total += deg[s];
+  for (uint32_t s = 0; s < a; ++s) total += rc.deg[s];
   const unsigned long long at = atomicAdd(v.nbr_used, total);
   if (at + total > v.nbr_cap) {  // pool exhausted: this trajectory iterates over all partners
     for (uint32_t s = 0; s < a; ++s) v.nbr_cnt[m.first + s] = NBR_ALL;
@@ -388,48 +420,41 @@ __device__ inline void build_partner_lists(const DevView &v, const TrajMeta &m, 
   for (uint32_t j = 0; j < a; ++j) {
     v.nbr_start[m.first + j] = (uint32_t)cursor;
     uint32_t n = 0;
-    const double rj = reach(j);
-    for (uint32_t k = 0; k < a && n < deg[j]; ++k)
-      if (k != j && dist(j, k) - d_far <= rj + reach(k)) v.nbr_pool[cursor + n++] = (uint8_t)k;
+    for (uint32_t k = 0; k < a && n < rc.deg[j]; ++k)
+      if (k != j && rc.linked(j, k)) v.nbr_pool[cursor + n++] = (uint8_t)k;
     v.nbr_cnt[m.first + j] = n;
-    cursor += deg[j];
+    cursor += rc.deg[j];
   }
 }
 
-// List the active particles, choose the bin, and fix the step at which the segment ends.
-__device__ inline int schedule_segment(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap) {
-  uint32_t s = 0;
-  for (uint32_t j = 0; j < m.no; ++j)
-    if (!v.particles[m.first + j].success) v.act[m.first + s++] = j;
-  int bin = bin_of(m.n_active);
-  const uint32_t horizon = free_flight_horizon(v, m);
-  // A short guaranteed horizon (a pair hovering just outside the table) would make the pass
-  // advance this trajectory by a few steps only: the full kernel's fixed-length segment is the
-  // better deal below a quarter of it.
-  // The longest fixed-length tier the guaranteed horizon covers; a horizon shorter than the
-  // shortest tier (a pair hovering just outside the table) goes to the full kernel.
-  for (int tier = N_FREE_TIERS - 1; tier >= (sg.drain ? 1 : 0); --tier)
-    if (horizon >= sg.of_bin[BIN_FREE + tier]) { bin = BIN_FREE + tier; break; }
-  uint32_t stop = m.steps + sg.of_bin[bin];
-  if (stop < m.steps) stop = 0xffffffffu;
-  // the criterion already holds before the first step: the reference still runs exactly
-  // one iteration (do-while shape of simulation.c:466-469, Q2)
-  if (m.steps == 0 && all_paired(m.no, m.n_flagged)) stop = 1;
-  if (stop > v.c.max_steps) stop = v.c.max_steps;
-  if (stop > step_cap) stop = step_cap;
-  m.step_stop = stop;
-  if (bin >= BIN_FREE) m.status = ST_FLYING;
-  if (bin >= BIN_WARP1 && bin <= BIN_WARP4 && stop > m.steps) build_partner_lists(v, m, stop - m.steps);
-  return bin;
+// What a resolve thread wants launched for its trajectory this pass.
+struct Schedule {
+  int bin = -1;            // bin of the trajectory (or of its core); -1: nothing for the integrate kernels
+  int fly_tier = -1;       // free-flight list to append to; -1: nobody flies
+  uint32_t fly_first = 0;  // first slot of the act list that flies
+  uint32_t fly_count = 0;
+};
+
+// core-loner and loner-loner pair-steps (never evaluated: provably force-free) for the core
+// steps taken since the last call
+__device__ inline void account_cross_pairs(TrajMeta &m, Counters &work) {
+  if (m.n_loners && m.steps > m.cross_from) {
+    const unsigned long long l = m.n_loners, c = m.n_active;
+    const unsigned long long n = (unsigned long long)(m.steps - m.cross_from) * (l * c + l * (l - 1) / 2);
+    work.pair_steps += n;
+    work.pair_skipped += n;
+  }
+  m.cross_from = m.steps;
 }
 
-// Commit a free-flight segment (the kernel leaves TrajMeta alone): the trajectory is now at
-// step_stop; its clock is the one the particles carry.
+// Commit a whole-trajectory free-flight segment (the kernel leaves TrajMeta alone): the
+// trajectory is now at step_stop; its clock is the one the particles carry.
 __device__ inline void land_free_flight(const DevView &v, TrajMeta &m, Counters &work) {
   const unsigned long long k = m.step_stop - m.steps;
   m.steps = m.step_stop;
   m.time = v.particles[m.first + v.act[m.first]].time;
   m.status = ST_LIVE;
+  m.cross_from = m.steps;
   const unsigned long long a = m.n_active;
   work.particle_steps += k * a;
   work.pair_steps += k * (a * (a - 1) / 2);
@@ -437,25 +462,185 @@ __device__ inline void land_free_flight(const DevView &v, TrajMeta &m, Counters 
   work.free_steps += k * a;
 }
 
-// Warp-aggregated append of trajectory t to bin `bin` (-1 = none): one atomic per
-// (warp, bin).  Must be called by all 32 lanes.  The free-flight bin takes one entry per
-// moving PARTICLE: (trajectory, slot in its active list).
-__device__ inline void append_to_bin(int bin, uint32_t t, uint32_t n_active, uint32_t stride,
-                                     uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list,
-                                     uint2 *__restrict__ free_list, uint32_t free_stride) {
+// The trajectory ends at step m.steps (success at a core meeting) while its loners are ahead
+// at loner_until: the loop of the reference stops for everybody at that step, so put the
+// loners where they were then -- re-fly them from their take-off orientation.  (With the
+// `==` criterion at most one particle is still moving at that point.)
+template <class P>
+__device__ inline void rewind_loners(const DevView &v, TrajMeta &m, Counters &work) {
+  const Consts &c = v.c;
+  heroam_particle *base = v.particles + m.first;
+  const uint32_t *act = v.act + m.first;
+  for (uint32_t i = 0; i < m.n_loners; ++i) {
+    const uint32_t j = act[m.core_slots + i];
+    heroam_particle *p = base + j;
+    const float4 q4 = v.ckpt_q[m.first + j];
+    float q[4] = {q4.x, q4.y, q4.z, q4.w}, w[3], w_rec[3], r[3], vel[3], v2;
+    ld3(p->ang_velocity, w_rec);
+    load_w<P>(c, w_rec, w);
+    float time = m.loner_time0;
+    for (uint32_t k = m.loner_from; k < m.steps; ++k) {
+      advance_orientation<P>(c, w, q);
+      time = __fadd_rn(time, c.dt);
+    }
+    pole_position<P>(c, q, r);
+    stored_velocity<P>(r, w_rec, vel, v2);
+    p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
+    st3(p->position, r);
+    st3(p->velocity, vel);
+    p->velocity_sq = v2;
+    p->time = time;
+  }
+  const unsigned long long undone = (unsigned long long)(m.loner_until - m.steps) * m.n_loners;
+  work.particle_steps -= undone;  // unsigned wrap-around: the per-run sums come out right
+  work.free_steps -= undone;
+  m.loner_until = m.steps;
+}
+
+// Everything a resolve thread does for a live trajectory before scheduling: finish a pending
+// meeting step, land a whole-trajectory flight, account work, let an emptied core jump to its
+// loners.
+template <class P>
+__device__ inline void settle(const DevView &v, TrajMeta &m, Counters &work) {
+  if (m.status == ST_MIDSTEP) {
+    account_cross_pairs(m, work);   // steps before the meeting, old core size
+    finish_step<P>(v, m, work);
+    account_cross_pairs(m, work);   // the meeting step itself, surviving core
+  } else if (m.status == ST_FLYING) {
+    land_free_flight(v, m, work);
+  } else {
+    account_cross_pairs(m, work);
+  }
+}
+
+// List the moving particles, decide who flies and who is integrated, choose the bin, and fix
+// the step at which the segment ends.
+__device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap,
+                                            Counters &work) {
+  Schedule out;
+  heroam_particle *base = v.particles + m.first;
+  uint32_t *act = v.act + m.first;
+  // ---- loners ahead of the core: the core catches up on its own -------------------------------
+  if (m.n_loners && m.steps < m.loner_until) {
+    uint32_t lon[MAX_ACTIVE];
+    for (uint32_t i = 0; i < m.n_loners; ++i) lon[i] = act[m.core_slots + i];
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < m.no; ++j) {
+      if (base[j].success) continue;
+      bool is_loner = false;
+      for (uint32_t i = 0; i < m.n_loners; ++i) is_loner = is_loner || lon[i] == j;
+      if (!is_loner) act[s++] = j;
+    }
+    m.core_slots = s;  // == m.n_active
+    for (uint32_t i = 0; i < m.n_loners; ++i) act[s + i] = lon[i];
+    if (m.n_active > 0) {
+      uint32_t stop = m.steps + sg.of_bin[BIN_CORE + (int)m.n_active];
+      if (stop < m.steps || stop > m.loner_until) stop = m.loner_until;
+      m.step_stop = stop;
+      out.bin = BIN_CORE + (int)m.n_active;
+      return out;
+    }
+    // nobody left in the core: its remaining steps up to the loners are empty steps
+    account_cross_pairs(m, work);
+    const unsigned long long l = m.n_loners;
+    const unsigned long long n = (unsigned long long)(m.loner_until - m.steps) * (l * (l - 1) / 2);
+    work.pair_steps += n;
+    work.pair_skipped += n;
+    m.steps = m.loner_until;
+    m.cross_from = m.steps;
+    m.time = base[lon[0]].time;
+  }
+  // ---- everybody at the same step: fresh analysis -----------------------------------------------
+  m.n_active += m.n_loners;
+  m.n_loners = 0;
+  uint32_t a = 0;
+  for (uint32_t j = 0; j < m.no; ++j)
+    if (!base[j].success) act[a++] = j;
+  m.core_slots = a;
+  const bool one_step_only = m.steps == 0 && all_paired(m.no, m.n_flagged);  // Q2
+  auto clip = [&](uint32_t stop) {
+    if (stop < m.steps) stop = 0xffffffffu;
+    if (one_step_only) stop = 1;
+    if (stop > v.c.max_steps) stop = v.c.max_steps;
+    if (stop > step_cap) stop = step_cap;
+    return stop;
+  };
+  // (1) the whole trajectory in free flight: the longest fixed-length tier its horizon covers
+  const uint32_t horizon = free_flight_horizon(v, m);
+  for (int tier = 2; tier >= (sg.drain ? 1 : 0); --tier)
+    if (horizon >= sg.of_bin[BIN_FREE + tier]) {
+      m.step_stop = clip(m.steps + sg.of_bin[BIN_FREE + tier]);
+      m.status = ST_FLYING;
+      out.fly_tier = tier;
+      out.fly_first = 0;
+      out.fly_count = a;
+      return out;
+    }
+  // (2) split: particles linked to nobody for the window fly alone, the rest is the core
+  const uint32_t window = sg.of_bin[BIN_FREE + FREE_SPLIT];
+  if (a >= 2 && a <= (uint32_t)MAX_ACTIVE && window >= 64u) {
+    Reach rc;
+    rc.init(v, m, a, window);
+    rc.solve();
+    uint32_t n_core = 0, n_lon = 0;
+    uint32_t core[MAX_ACTIVE], lon[MAX_ACTIVE];
+    for (uint32_t s = 0; s < a; ++s) {
+      if (rc.deg[s] == 0 && rc.force_free(s)) lon[n_lon++] = act[s];
+      else core[n_core++] = act[s];
+    }
+    if (n_lon >= 1 && n_core <= (uint32_t)THREAD_MAX_A) {
+      for (uint32_t s = 0; s < n_core; ++s) act[s] = core[s];
+      for (uint32_t i = 0; i < n_lon; ++i) {
+        act[n_core + i] = lon[i];
+        const float *o = base[lon[i]].orientation;
+        v.ckpt_q[m.first + lon[i]] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      const uint32_t stop = clip(m.steps + window);
+      m.n_active = n_core;
+      m.core_slots = n_core;
+      m.n_loners = n_lon;
+      m.loner_from = m.steps;
+      m.loner_until = stop;
+      m.loner_time0 = m.time;
+      m.cross_from = m.steps;
+      m.step_stop = stop;
+      const unsigned long long flown = (unsigned long long)(stop - m.steps) * n_lon;
+      work.particle_steps += flown;
+      work.free_steps += flown;
+      out.bin = n_core ? BIN_CORE + (int)n_core : -1;
+      out.fly_tier = FREE_SPLIT;
+      out.fly_first = n_core;
+      out.fly_count = n_lon;
+      return out;
+    }
+  }
+  // (3) the whole trajectory in the kernel of its moving count
+  out.bin = bin_of(a);
+  m.step_stop = clip(m.steps + sg.of_bin[out.bin]);
+  if (out.bin >= BIN_WARP1 && out.bin <= BIN_WARP4 && m.step_stop > m.steps) build_partner_lists(v, m, m.step_stop - m.steps);
+  return out;
+}
+
+// Append what a resolve thread scheduled.  Integrate bins: warp-aggregated, one atomic per
+// (warp, bin); must be called by all 32 lanes.  Flyers: one entry per PARTICLE, (trajectory,
+// slot in its act list).
+__device__ inline void append_schedule(const Schedule &sc, uint32_t t, uint32_t stride, uint32_t *__restrict__ bin_count,
+                                       uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list,
+                                       uint32_t free_stride) {
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned peers = __match_any_sync(0xffffffffu, bin);
-  if (bin >= 0 && bin < BIN_FREE) {
+  const unsigned peers = __match_any_sync(0xffffffffu, sc.bin);
+  if (sc.bin >= 0) {
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(bin_count + bin, (uint32_t)__popc(peers));
+    if ((int)lane == leader) base = atomicAdd(bin_count + sc.bin, (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    bin_list[(size_t)bin * stride + base + rank] = t;
-  } else if (bin >= BIN_FREE) {
-    const uint32_t base = atomicAdd(bin_count + bin, n_active);
-    uint2 *list = free_list + (size_t)(bin - BIN_FREE) * free_stride;
-    for (uint32_t s = 0; s < n_active; ++s) list[base + s] = make_uint2(t, s);
+    bin_list[(size_t)sc.bin * stride + base + rank] = t;
+  }
+  if (sc.fly_tier >= 0 && sc.fly_count) {
+    const uint32_t base = atomicAdd(bin_count + BIN_FREE + sc.fly_tier, sc.fly_count);
+    uint2 *list = free_list + (size_t)sc.fly_tier * free_stride;
+    for (uint32_t s = 0; s < sc.fly_count; ++s) list[base + s] = make_uint2(t, sc.fly_first + s);
   }
 }
 
@@ -466,7 +651,7 @@ __device__ inline void flush_work(const DevView &v, const Counters &work) {
   const unsigned long long un = warp_sum_u64(work.unsupported);
   const unsigned long long sk = warp_sum_u64(work.pair_skipped);
   const unsigned long long fs = warp_sum_u64(work.free_steps);
-  if ((threadIdx.x & 31u) == 0 && (ps | pr | ir | un)) {
+  if ((threadIdx.x & 31u) == 0 && (ps | pr | ir | un | fs)) {
     atomicAdd(&v.counters->particle_steps, ps);
     atomicAdd(&v.counters->pair_steps, pr);
     atomicAdd(&v.counters->inrange_steps, ir);
@@ -476,45 +661,49 @@ __device__ inline void flush_work(const DevView &v, const Counters &work) {
   }
 }
 
+// One resolve visit of a live trajectory: returns what to launch for it (nothing if it ended).
+template <class P>
+__device__ inline Schedule resolve_live(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap,
+                                        Counters &work) {
+  settle<P>(v, m, work);
+  const uint32_t done = evaluate_exit(v.c, m, step_cap);
+  if (done != NOT_DONE) {
+    if (m.n_loners && m.loner_until > m.steps) rewind_loners<P>(v, m, work);
+    m.status = ST_DONE + done;
+    if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported += 1;
+    return Schedule();
+  }
+  return schedule_segment(v, m, sg, step_cap, work);
+}
+
 // ---------------------------------------------------------------------------------
 // k_resolve_and_bin: one thread per trajectory, once per pass (fixed batch).
-//   1. finish a pending meeting step;
-//   2. evaluate the exit conditions;
-//   3. schedule the next segment and append the trajectory to the bin of its active count.
 // ---------------------------------------------------------------------------------
 template <class P>
 __global__ void k_resolve_and_bin(DevView v, Segments sg, uint32_t step_cap, uint32_t *__restrict__ bin_count,
                                   uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   Counters work = {};
-  int bin = -1;
-  uint32_t n_active = 0;
+  Schedule sc;
   if (t < v.n_traj) {
     TrajMeta m = v.meta[t];
     if (m.status < ST_DONE) {
-      if (m.status == ST_MIDSTEP) finish_step<P>(v, m, work);
-      else if (m.status == ST_FLYING) land_free_flight(v, m, work);
-      const uint32_t done = evaluate_exit(v.c, m, step_cap);
-      if (done != NOT_DONE) {
-        m.status = ST_DONE + done;
-        if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported = 1;
-      } else {
-        bin = schedule_segment(v, m, sg, step_cap);
-        n_active = m.n_active;
-      }
+      sc = resolve_live<P>(v, m, sg, step_cap, work);
       v.meta[t] = m;
     }
   }
-  append_to_bin(bin, t, n_active, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
+  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
   flush_work(v, work);
 }
 
 // ---------------------------------------------------------------------------------
-// k_free_flight: one thread per moving PARTICLE of a trajectory whose pairs are all out of
-// reach for the whole segment.  Zero force: the half kicks add +-0, w stays what it is, and a
-// step is nothing but the orientation update; the position (only needed by the pair loop)
-// is rebuilt once at the end.  Per step this performs exactly the operations the full
-// kernels perform on that particle, so the records it leaves are bit-identical.
+// k_free_flight: one thread per flying PARTICLE.  Zero force: the half kicks add +-0, w stays
+// what it is, and a step is nothing but the orientation update; the position (only needed by
+// the pair loop) is rebuilt once at the end.  Per step this performs exactly the operations
+// the full kernels perform on that particle, so the records it leaves are bit-identical.
+// Flyers are either all moving particles of a trajectory (they fly [steps, step_stop)) or the
+// loners of a split trajectory (act slots >= n_active; they fly [loner_from, loner_until)).
+// TrajMeta is only read, and only fields no concurrent core kernel changes.
 // ---------------------------------------------------------------------------------
 template <class P>
 __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__restrict__ list, uint32_t count) {
@@ -522,14 +711,18 @@ __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__r
   if (item >= count) return;
   const Consts &c = v.c;
   const uint2 e = list[item];
-  const TrajMeta m = v.meta[e.x];  // read only: the next resolve pass commits steps and time
-  heroam_particle *p = v.particles + m.first + v.act[m.first + e.y];
+  const TrajMeta *m = v.meta + e.x;
+  const uint32_t first = m->first;
+  const bool loner = m->n_loners != 0u;  // whole-trajectory flights have none
+  const uint32_t from = loner ? m->loner_from : m->steps;
+  const uint32_t until = loner ? m->loner_until : m->step_stop;
+  float time = loner ? m->loner_time0 : m->time;
+  heroam_particle *p = v.particles + first + v.act[first + e.y];
   float q[4] = {p->orientation[0], p->orientation[1], p->orientation[2], p->orientation[3]};
   float w[3], w_rec[3];
   ld3(p->ang_velocity, w_rec);
   load_w<P>(c, w_rec, w);
-  float time = m.time;
-  for (uint32_t k = m.steps; k < m.step_stop; ++k) {
+  for (uint32_t k = from; k < until; ++k) {
     advance_orientation<P>(c, w, q);
     time = __fadd_rn(time, c.dt);
   }

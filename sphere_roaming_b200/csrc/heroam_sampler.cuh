@@ -293,6 +293,7 @@ __global__ void k_pool_init(DevView v, uint32_t cap) {
   TrajMeta m;
   m.first = t * cap;
   m.no = 0; m.steps = 0; m.time = 0.0f; m.n_flagged = 0; m.n_active = 0; m.step_stop = 0;
+  m.n_loners = 0; m.loner_from = 0; m.loner_until = 0; m.loner_time0 = 0.0f; m.cross_from = 0; m.core_slots = 0;
   m.status = ST_FREE;
   v.meta[t] = m;
 }
@@ -303,19 +304,14 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
                                uint2 *__restrict__ free_list) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   Counters work = {};
-  int bin = -1;
-  uint32_t n_active = 0;
+  Schedule sc;
   if (t < v.n_traj) {
     TrajMeta m = v.meta[t];
-    if (m.status == ST_MIDSTEP) finish_step<P>(v, m, work);
-    else if (m.status == ST_FLYING) land_free_flight(v, m, work);
     // a freshly spawned trajectory can be over at once (nobody moving), hence the loop
     for (;;) {
       if (m.status < ST_DONE) {
-        const uint32_t done = evaluate_exit(v.c, m, step_cap);
-        if (done == NOT_DONE) break;
-        m.status = ST_DONE + done;
-        if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported += 1;
+        sc = resolve_live<P>(v, m, sg, step_cap, work);
+        if (m.status < ST_DONE) break;  // still live: scheduled
       }
       if (m.status != ST_FREE) {
         accumulate_stats(v, m, pool.stats);
@@ -327,6 +323,7 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
       g.begin(pool.sp.seed, pool.sp.he_number, pool.sp.first_index + idx);
       const uint32_t n = sample_count(g, pool.sp.limit);
       m.no = n; m.steps = 0; m.time = 0.0f; m.n_flagged = 0; m.step_stop = 0;
+      m.n_loners = 0; m.loner_from = 0; m.loner_until = 0; m.loner_time0 = 0.0f; m.cross_from = 0; m.core_slots = 0;
       if (n > pool.cap) {  // does not fit a slot: counted, not integrated
         m.no = 0; m.n_active = 0;
         m.status = ST_DONE + HEROAM_DONE_UNSUPPORTED;
@@ -337,15 +334,12 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
       sample_trajectory(g, pool.sp, v.c, v.table, p, n);
       for (uint32_t j = 0; j < n; ++j) m.n_flagged += p[j].success ? 1u : 0u;
       m.n_active = n - m.n_flagged;
+      m.core_slots = m.n_active;
       m.status = ST_LIVE;
-    }
-    if (m.status < ST_DONE) {
-      bin = schedule_segment(v, m, sg, step_cap);
-      n_active = m.n_active;
     }
     v.meta[t] = m;
   }
-  append_to_bin(bin, t, n_active, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
+  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
   flush_work(v, work);
 }
 
@@ -505,9 +499,8 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
     if (live == 0) break;  // every slot is free and the index space is used up
     {
       uint64_t trajectories = 0;
-      for (int b = 1; b < BIN_FREE; ++b) trajectories += ctx->h_bin_count[b];
-      uint64_t flying = 0;
-      for (int b = BIN_FREE; b < N_BINS; ++b) flying += ctx->h_bin_count[b];
+      for (int b = 1; b < N_BINS; ++b)
+        if (b < BIN_FREE || b >= BIN_CORE) trajectories += ctx->h_bin_count[b];
       // fewer trajectories in the full kernels than fill the GPU once: latency-bound from here on
       draining = trajectories < (uint64_t)ctx->sm_count * 768;
     }
