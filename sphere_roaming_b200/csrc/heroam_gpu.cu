@@ -340,6 +340,14 @@ extern "C" int heroam_gpu_upload(heroam_ctx *ctx, unsigned long long he_number, 
   return HEROAM_OK;
 }
 
+// Longest window for which the acceleration part of the reach bound stays around 2 A per linked
+// partner: R dt^2 f_max / (m R) W^2 / 2 <= 2  =>  W <= 2 sqrt(m / f_max) / dt.
+static uint32_t split_window_max(const heroam_ctx *ctx) {
+  if (!(ctx->f_max > 0.0f)) return 0xffffffffu;
+  const double w = 2.0 * sqrt((double)ctx->conf.mass / (double)ctx->f_max) / (double)ctx->conf.dt;
+  return w > 4.0e9 ? 0xffffffffu : (uint32_t)w;
+}
+
 // the kappa-scaled copy of the table the Turbo kernels gather from
 static int refresh_scaled_table(heroam_ctx *ctx, const Consts &c) {
   if (ctx->table_kappa == c.kappa) return HEROAM_OK;
@@ -427,7 +435,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
-    Segments sg = make_segments(ctx->opt.segment_steps, draining);
+    Segments sg = make_segments(ctx->opt.segment_steps, draining, split_window_max(ctx));
     sg.free_stride = ctx->free_stride;
     k_resolve_and_bin<R><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());

@@ -270,7 +270,7 @@ struct Segments {
                           // the short free-flight tier would only slow per-pass progress
 };
 
-__host__ inline Segments make_segments(uint32_t base, bool drain) {
+__host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split_window_max) {
   Segments sg;
   auto scaled = [base](uint32_t num, uint32_t den) { uint32_t v = (uint32_t)((unsigned long long)base * num / den); return v ? v : 1u; };
   sg.of_bin[0] = base;
@@ -299,8 +299,11 @@ __host__ inline Segments make_segments(uint32_t base, bool drain) {
   sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
   sg.of_bin[BIN_FREE + 1] = scaled(2, 1);
   sg.of_bin[BIN_FREE + 2] = scaled(8, 1);
-  // split trajectories: core and loners advance by the same fixed window
-  const uint32_t window = drain ? scaled(2, 1) : scaled(1, 2);
+  // split trajectories: core and loners advance by the same fixed window.  The reach bound grows
+  // with the square of the window (possible acceleration), so beyond split_window_max =
+  // O(sqrt(m / f_max) / dt) everything would look linked to everything.
+  uint32_t window = scaled(1, 2);
+  while (window > split_window_max && window > 64u) window /= 2u;
   sg.of_bin[BIN_FREE + FREE_SPLIT] = window;
   for (int a = 0; a <= THREAD_MAX_A; ++a) sg.of_bin[BIN_CORE + a] = window;
   sg.free_stride = 0;
@@ -577,8 +580,10 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
       return out;
     }
   // (2) split: particles linked to nobody for the window fly alone, the rest is the core
+  // While draining, a narrow trajectory advances further per pass in the kernel of its size
+  // (longer segments) than split with the bounded window; wide ones always gain from splitting.
   const uint32_t window = sg.of_bin[BIN_FREE + FREE_SPLIT];
-  if (a >= 2 && a <= (uint32_t)MAX_ACTIVE && window >= 64u) {
+  if (a >= 2 && a <= (uint32_t)MAX_ACTIVE && window >= 64u && (!sg.drain || a > (uint32_t)THREAD_MAX_A)) {
     Reach rc;
     rc.init(v, m, a, window);
     rc.solve();
