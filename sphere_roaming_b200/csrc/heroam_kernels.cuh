@@ -328,7 +328,9 @@ struct Reach {
   const heroam_particle *base;
   const uint32_t *act;
   uint32_t a;
-  double R, dt, W, d_far, gain;
+  // single precision is enough: every bound carries 1 % (speeds, forces) plus absolute slack,
+  // orders of magnitude above float rounding (1e-7 relative, < 1e-4 A on these distances)
+  float RdtW, accel, slack, d_far;
   float w0[MAX_ACTIVE];
   uint8_t deg[MAX_ACTIVE];
 
@@ -336,33 +338,37 @@ struct Reach {
     base = v.particles + m.first;
     act = v.act + m.first;
     a = count;
-    R = (double)v.c.radius; dt = (double)v.c.dt; W = (double)window;
-    d_far = sqrt((double)v.c.far2);
-    gain = dt * (double)v.c.f_max * (double)v.c.inv_mr * 1.01;
+    const float R = v.c.radius, dt = v.c.dt, W = (float)window;
+    d_far = sqrtf(v.c.far2) * 1.00001f;
+    RdtW = R * dt * W * 1.01f;                                          // path per unit angular speed
+    accel = 0.5f * R * dt * dt * v.c.f_max * v.c.inv_mr * W * W * 1.02f; // extra path per linked partner
+    slack = 2.0e-6f * R * W + 2.0e-3f;
     for (uint32_t s = 0; s < a; ++s) {
       const float *w = base[act[s]].ang_velocity;
-      w0[s] = (float)(sqrt((double)w[0] * w[0] + (double)w[1] * w[1] + (double)w[2] * w[2]) * 1.01);
+      w0[s] = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
       deg[s] = 0;
     }
   }
-  __device__ double reach(uint32_t s) const {
-    return R * dt * ((double)w0[s] * W + 0.5 * gain * (double)deg[s] * W * W) + 2.0e-6 * R * W + 1.0e-3;
-  }
-  __device__ double dist(uint32_t j, uint32_t k) const {
+  __device__ float reach(uint32_t s) const { return fmaf(w0[s], RdtW, fmaf((float)deg[s], accel, slack)); }
+  __device__ float dist(uint32_t j, uint32_t k) const {
     const float *pj = base[act[j]].position, *pk = base[act[k]].position;
-    const double dx = (double)pj[0] - pk[0], dy = (double)pj[1] - pk[1], dz = (double)pj[2] - pk[2];
-    return sqrt(dx * dx + dy * dy + dz * dz);
+    const float dx = pj[0] - pk[0], dy = pj[1] - pk[1], dz = pj[2] - pk[2];
+    return sqrtf(dx * dx + dy * dy + dz * dz);
   }
   __device__ bool linked(uint32_t j, uint32_t k) const { return dist(j, k) - d_far <= reach(j) + reach(k); }
   __device__ void solve() {
     for (int iter = 0; iter < 16; ++iter) {
       bool grew = false;
-      for (uint32_t j = 0; j < a; ++j) {
-        uint32_t n = 0;
-        for (uint32_t k = 0; k < a; ++k)
-          if (k != j && linked(j, k)) ++n;
-        if (n > deg[j]) { deg[j] = (uint8_t)n; grew = true; }
+      // one sweep over unordered pairs: count links with the current reaches
+      uint8_t cnt[MAX_ACTIVE];
+      for (uint32_t s = 0; s < a; ++s) cnt[s] = 0;
+      for (uint32_t j = 0; j + 1 < a; ++j) {
+        const float rj = reach(j);
+        for (uint32_t k = j + 1; k < a; ++k)
+          if (dist(j, k) - d_far <= rj + reach(k)) { ++cnt[j]; ++cnt[k]; }
       }
+      for (uint32_t s = 0; s < a; ++s)
+        if (cnt[s] > deg[s]) { deg[s] = cnt[s]; grew = true; }
       if (!grew) return;
     }
     for (uint32_t s = 0; s < a; ++s) deg[s] = (uint8_t)(a - 1);  // no fixed point in time: link everything
@@ -382,27 +388,27 @@ __device__ inline uint32_t free_flight_horizon(const DevView &v, const TrajMeta 
   if (a == 0 || a > (uint32_t)FREE_MAX_A) return 0;
   const heroam_particle *base = v.particles + m.first;
   const uint32_t *act = v.act + m.first;
-  double px[FREE_MAX_A], py[FREE_MAX_A], pz[FREE_MAX_A], reach[FREE_MAX_A];
-  const double R = (double)v.c.radius, dt = (double)v.c.dt;
+  float px[FREE_MAX_A], py[FREE_MAX_A], pz[FREE_MAX_A], reach[FREE_MAX_A];
+  const float R = v.c.radius, dt = v.c.dt;
   for (uint32_t s = 0; s < a; ++s) {
     const heroam_particle *p = base + act[s];
     if (p->force[0] != 0.0f || p->force[1] != 0.0f || p->force[2] != 0.0f) return 0;
     px[s] = p->position[0]; py[s] = p->position[1]; pz[s] = p->position[2];
-    const double wx = p->ang_velocity[0], wy = p->ang_velocity[1], wz = p->ang_velocity[2];
-    reach[s] = sqrt(wx * wx + wy * wy + wz * wz) * R * dt * 1.01 + 2.0e-6 * R;
+    const float wx = p->ang_velocity[0], wy = p->ang_velocity[1], wz = p->ang_velocity[2];
+    reach[s] = sqrtf(wx * wx + wy * wy + wz * wz) * R * dt * 1.01f + 2.0e-6f * R;  // per step
   }
   if (a == 1) return 0xffffffffu;
-  const double d_far = sqrt((double)v.c.far2);
-  double horizon = 4.0e9;
+  const float d_far = sqrtf(v.c.far2) * 1.00001f + 1.0e-3f;
+  float horizon = 4.0e9f;
   for (uint32_t j = 0; j + 1 < a; ++j)
     for (uint32_t k = j + 1; k < a; ++k) {
-      const double dx = px[j] - px[k], dy = py[j] - py[k], dz = pz[j] - pz[k];
-      const double gap = sqrt(dx * dx + dy * dy + dz * dz) - d_far;
-      if (!(gap > 0.0)) return 0;
-      const double h = gap / (reach[j] + reach[k]) - 2.0;
+      const float dx = px[j] - px[k], dy = py[j] - py[k], dz = pz[j] - pz[k];
+      const float gap = sqrtf(dx * dx + dy * dy + dz * dz) - d_far;
+      if (!(gap > 0.0f)) return 0;
+      const float h = gap / (reach[j] + reach[k]) * 0.999f - 2.0f;
       if (h < horizon) horizon = h;
     }
-  return horizon < 1.0 ? 0u : (horizon > 4.0e9 ? 0xffffffffu : (uint32_t)horizon);
+  return horizon < 1.0f ? 0u : (horizon > 4.0e9f ? 0xffffffffu : (uint32_t)horizon);
 }
 
 // Partner lists for the warp-per-trajectory kernels: slot s's list holds, in ascending order,
