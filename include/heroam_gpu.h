@@ -79,7 +79,7 @@ typedef struct heroam_options {
                              above; 1 = the slow record-resident kernel (cross-check only);
                              2 = warp-per-trajectory for everything above 8 (cross-check);
                              3 = shared-memory kernel for 9..16 (cross-check)                  */
-  unsigned int pool_slots; /* trajectories kept in flight by heroam_gpu_run_stats (0 = 2^21)        */
+  unsigned int pool_slots; /* trajectories kept in flight by heroam_gpu_run_stats (0 = 2^22)        */
   int count_work;         /* fast mode only: 1 = the integrate kernels also count in-range pair-steps
                              (heroam_run_info.inrange_steps) at ~3 % cost; exact mode always counts   */
   int reserved[1];

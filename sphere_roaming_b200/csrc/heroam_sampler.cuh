@@ -543,7 +543,7 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
     return fail(HEROAM_E_ARG, "mean excitation number %g outside (0, 700]: Knuth's product of uniforms "
                 "(simulation.c:257-275) is undefined there", lambda);
   const uint32_t cap = pool_slot_capacity(lambda);
-  const unsigned long long pool_max = ctx->opt.pool_slots > 0 ? (unsigned long long)ctx->opt.pool_slots : (1ull << 21);
+  const unsigned long long pool_max = ctx->opt.pool_slots > 0 ? (unsigned long long)ctx->opt.pool_slots : (1ull << 22);
   const uint32_t slots = (uint32_t)(count < pool_max ? count : pool_max);
   rc = reserve(ctx, slots, (size_t)slots * cap);
   if (rc) return rc;

@@ -216,6 +216,25 @@ class Engine:
                                                       out.ctypes.data, len(counts), res.ctypes.data))
         return out, res
 
+    def simulate_inplace(self, he_number: int, counts: np.ndarray, flat: np.ndarray, results: np.ndarray) -> None:
+        """``heroam_gpu_simulate_flat`` on caller-owned (e.g. page-locked) buffers, in place."""
+        assert counts.dtype == np.uint32 and flat.dtype == PARTICLE_DTYPE and results.dtype == RESULT_DTYPE
+        assert counts.flags.c_contiguous and flat.flags.c_contiguous and results.flags.c_contiguous
+        self._check(self.lib.heroam_gpu_simulate_flat(self.handle, he_number, counts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                      flat.ctypes.data, len(counts), results.ctypes.data))
+
+    def sample_into(self, he_number: int, count: int, first_index: int, counts: np.ndarray, flat: np.ndarray) -> int:
+        """``heroam_gpu_sample_flat`` into caller-owned buffers; returns the number of records
+        (raises if the buffer is too small)."""
+        total = C.c_long(0)
+        self._check(self.lib.heroam_gpu_sample_flat(self.handle, he_number, first_index, count,
+                                                    counts.ctypes.data_as(C.POINTER(C.c_uint32)), flat.ctypes.data,
+                                                    len(flat), C.byref(total)))
+        if total.value > len(flat):
+            raise HeroamError(f"sample_into: buffer of {len(flat)} records, {total.value} needed")
+        self._n = (count, total.value)
+        return int(total.value)
+
     def upload(self, he_number: int, counts: np.ndarray, flat: np.ndarray) -> None:
         counts = np.ascontiguousarray(counts, dtype=np.uint32)
         flat = np.ascontiguousarray(flat)
