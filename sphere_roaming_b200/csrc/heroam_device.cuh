@@ -185,9 +185,9 @@ __device__ __forceinline__ float rsqrt_raw(float x) {  // one MUFU.RSQ, operands
 // Conversions between the particle records (w, F) and the state a kernel keeps.
 template <class P>
 __device__ __forceinline__ void load_w(const Consts &c, const float *src, float w[3]) {
-  w[0] = P::turbo ? src[0] * c.half_dt : src[0];
-  w[1] = P::turbo ? src[1] * c.half_dt : src[1];
-  w[2] = P::turbo ? src[2] * c.half_dt : src[2];
+  w[0] = P::turbo ? __fmul_rn(src[0], c.half_dt) : src[0];
+  w[1] = P::turbo ? __fmul_rn(src[1], c.half_dt) : src[1];
+  w[2] = P::turbo ? __fmul_rn(src[2], c.half_dt) : src[2];
 }
 template <class P>
 __device__ __forceinline__ void unscale_w(const Consts &c, const float w[3], float out[3]) {
@@ -197,9 +197,9 @@ __device__ __forceinline__ void unscale_w(const Consts &c, const float w[3], flo
 }
 template <class P>
 __device__ __forceinline__ void load_f(const Consts &c, const float *src, float f[3]) {
-  f[0] = P::turbo ? src[0] * c.kappa : src[0];
-  f[1] = P::turbo ? src[1] * c.kappa : src[1];
-  f[2] = P::turbo ? src[2] * c.kappa : src[2];
+  f[0] = P::turbo ? __fmul_rn(src[0], c.kappa) : src[0];
+  f[1] = P::turbo ? __fmul_rn(src[1], c.kappa) : src[1];
+  f[2] = P::turbo ? __fmul_rn(src[2], c.kappa) : src[2];
 }
 template <class P>
 __device__ __forceinline__ void unscale_f(const Consts &c, const float f[3], float out[3]) {
@@ -227,9 +227,9 @@ __device__ __forceinline__ void half_kick(const Consts &c, const float r[3], con
   } else if (P::turbo) {  // F' already carries (dt/2)^2/(m R^2): this is (dt/2) * (half kick)
     hk[0] = tx; hk[1] = ty; hk[2] = tz;
   } else {
-    hk[0] = tx * c.kick;
-    hk[1] = ty * c.kick;
-    hk[2] = tz * c.kick;
+    hk[0] = __fmul_rn(tx, c.kick);  // not contractable into w + hk
+    hk[1] = __fmul_rn(ty, c.kick);
+    hk[2] = __fmul_rn(tz, c.kick);
   }
 }
 
@@ -265,7 +265,9 @@ __device__ __forceinline__ void advance_orientation(const Consts &c, const float
     const float ny = qy + fmaf(oz, qx, fmaf(-ox, qz, oy * qa));
     const float nz = qz + fmaf(oz, qa, fmaf(-oy, qx, ox * qy));
     const float inv = rsqrt_raw(fmaf(nz, nz, fmaf(ny, ny, fmaf(nx, nx, na * na))));
-    q[0] = na * inv; q[1] = nx * inv; q[2] = ny * inv; q[3] = nz * inv;
+    // __fmul_rn: a plain product could be contracted by the compiler into whatever addition
+    // consumes it next (differently in different kernels); the state must not depend on that
+    q[0] = __fmul_rn(na, inv); q[1] = __fmul_rn(nx, inv); q[2] = __fmul_rn(ny, inv); q[3] = __fmul_rn(nz, inv);
   } else {
     const float ta = -fmaf(oz, qz, fmaf(oy, qy, ox * qx));
     const float tx = fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
@@ -276,7 +278,7 @@ __device__ __forceinline__ void advance_orientation(const Consts &c, const float
     const float ny = fmaf(ty, c.half_dt, qy);
     const float nz = fmaf(tz, c.half_dt, qz);
     const float inv = rsqrtf(P::dot4(na, nx, ny, nz));
-    q[0] = na * inv; q[1] = nx * inv; q[2] = ny * inv; q[3] = nz * inv;
+    q[0] = __fmul_rn(na, inv); q[1] = __fmul_rn(nx, inv); q[2] = __fmul_rn(ny, inv); q[3] = __fmul_rn(nz, inv);
   }
 }
 
@@ -298,14 +300,14 @@ __device__ __forceinline__ void pole_position(const Consts &c, const float q[4],
     r[1] = P::mul(ry, c.radius);
     r[2] = P::mul(rz, c.radius);
   } else if (P::turbo) {  // unit q: a^2 - x^2 - y^2 + z^2 = 1 - 2 (x^2 + y^2)
-    r[0] = c.radius2 * fmaf(nx, nz, na * ny);
-    r[1] = c.radius2 * fmaf(ny, nz, -(na * nx));
+    r[0] = __fmul_rn(c.radius2, fmaf(nx, nz, na * ny));  // never contracted into the pair separations
+    r[1] = __fmul_rn(c.radius2, fmaf(ny, nz, -(na * nx)));
     r[2] = fmaf(-c.radius2, fmaf(nx, nx, ny * ny), c.radius);
   } else {
     // unit q: q (0,0,1) q^-1 = (2(xz + ay), 2(yz - ax), a^2 - x^2 - y^2 + z^2)
-    r[0] = c.radius2 * fmaf(nx, nz, na * ny);
-    r[1] = c.radius2 * fmaf(ny, nz, -(na * nx));
-    r[2] = c.radius * (fmaf(na, na, nz * nz) - fmaf(nx, nx, ny * ny));
+    r[0] = __fmul_rn(c.radius2, fmaf(nx, nz, na * ny));
+    r[1] = __fmul_rn(c.radius2, fmaf(ny, nz, -(na * nx)));
+    r[2] = __fmul_rn(c.radius, __fsub_rn(fmaf(na, na, nz * nz), fmaf(nx, nx, ny * ny)));
   }
 }
 

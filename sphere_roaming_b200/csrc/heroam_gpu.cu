@@ -360,7 +360,7 @@ static int refresh_scaled_table(heroam_ctx *ctx, const Consts &c) {
 }
 
 template <class P>
-static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) {
+static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, bool draining = false) {
   const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
@@ -369,7 +369,16 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt) 
     CU(cudaGetLastError());
     return HEROAM_OK;
   }
-  switch (bin >= BIN_CORE ? bin - BIN_CORE : bin) {  // the core of a split trajectory runs in the kernel of its size
+  const int width = bin >= BIN_CORE ? bin - BIN_CORE : bin;  // the core of a split trajectory runs in the kernel of its size
+  static const bool lookahead_on = !(getenv("HEROAM_LOOKAHEAD") && atoi(getenv("HEROAM_LOOKAHEAD")) == 0);
+  if (draining && lookahead_on && width >= 2 && width <= 4) {  // latency-bound: gather one step ahead (see k_integrate_thread)
+    if (width == 2) k_integrate_thread<2, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
+    else if (width == 3) k_integrate_thread<3, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
+    else k_integrate_thread<4, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
+    CU(cudaGetLastError());
+    return HEROAM_OK;
+  }
+  switch (width) {
     case 1: k_integrate_thread<1, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
     case 2: k_integrate_thread<2, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
     case 3: k_integrate_thread<3, P><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt); break;
@@ -465,7 +474,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
       if (!cnt) continue;
       // the bin streams start after ev_i0, i.e. after this pass's resolve kernel
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<H>(ctx, v, b, cnt);
+      int rc = launch_bin<H>(ctx, v, b, cnt, draining);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));

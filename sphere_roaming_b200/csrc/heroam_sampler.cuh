@@ -514,7 +514,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
       const uint32_t cnt = ctx->h_bin_count[b];
       if (!cnt) continue;
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<H>(ctx, v, b, cnt);
+      int rc = launch_bin<H>(ctx, v, b, cnt, draining);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
