@@ -32,6 +32,14 @@ static int fail(int code, const char *fmt, ...) {
                   __FILE__, __LINE__);                                                  \
   } while (0)
 
+// a device allocation that is released on every exit path of the function owning it
+template <class T>
+struct DevBuf {
+  T *ptr = nullptr;
+  ~DevBuf() { if (ptr) cudaFree(ptr); }
+  cudaError_t alloc(size_t count) { return cudaMalloc(&ptr, count * sizeof(T)); }
+};
+
 // ---------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------
@@ -596,8 +604,9 @@ extern "C" void heroam_gpu_free_particles(heroam_particles *p) {
 extern "C" int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_clock_mhz) {
   if (!ctx || !tflops) return fail(HEROAM_E_ARG, "null argument");
   CU(cudaSetDevice(ctx->device));
-  float *d_out = nullptr;
-  CU(cudaMalloc(&d_out, sizeof(float)));
+  DevBuf<float> out_buf;
+  CU(out_buf.alloc(1));
+  float *d_out = out_buf.ptr;
   const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
@@ -612,7 +621,6 @@ extern "C" int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_
     const double tf = flops / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }
-  cudaFree(d_out);
   *tflops = best;
   if (sm_clock_mhz) {
     int khz = 0;

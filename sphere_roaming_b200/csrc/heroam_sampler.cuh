@@ -550,10 +550,12 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
   ctx->he_number = he_number;
   ctx->n_traj = slots;
   ctx->n_particles = (size_t)slots * cap;
-  DevStats *d_stats = nullptr;
-  unsigned long long *d_cursor = nullptr;
-  CU(cudaMalloc(&d_stats, sizeof(DevStats)));
-  CU(cudaMalloc(&d_cursor, sizeof(unsigned long long)));
+  DevBuf<DevStats> stats_buf;
+  DevBuf<unsigned long long> cursor_buf;
+  CU(stats_buf.alloc(1));
+  CU(cursor_buf.alloc(1));
+  DevStats *d_stats = stats_buf.ptr;
+  unsigned long long *d_cursor = cursor_buf.ptr;
   PoolParams pool;
   pool.sp.seed = (long long)ctx->conf.seed;
   pool.sp.he_number = he_number;
@@ -606,7 +608,5 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
                 MAX_ACTIVE);
   }
   free(h);
-  cudaFree(d_stats);
-  cudaFree(d_cursor);
   return rc;
 }
