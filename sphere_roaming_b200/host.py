@@ -30,6 +30,23 @@ def load_library() -> C.CDLL:
         L.heroam_write_forcelist.argtypes = [C.c_char_p, C.POINTER(Config), C.POINTER(C.c_float), C.c_long]
         L.heroam_write_particlefile.restype = C.c_int
         L.heroam_write_particlefile.argtypes = [C.c_char_p, C.POINTER(ParticlesC), C.c_int]
+        L.heroam_h5_create.restype = C.c_void_p
+        L.heroam_h5_create.argtypes = [C.c_char_p]
+        L.heroam_h5_save_timestep.restype = C.c_int
+        L.heroam_h5_save_timestep.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+        L.heroam_h5_close.restype = C.c_int
+        L.heroam_h5_close.argtypes = [C.c_void_p]
+        L.heroam_h5_open.restype = C.c_void_p
+        L.heroam_h5_open.argtypes = [C.c_char_p]
+        L.heroam_h5_num_steps.restype = C.c_long
+        L.heroam_h5_num_steps.argtypes = [C.c_void_p]
+        L.heroam_h5_read_timestep.restype = C.c_int
+        L.heroam_h5_read_timestep.argtypes = [C.c_void_p, C.c_uint, C.POINTER(ParticlesC)]
+        L.heroam_h5_reader_close.restype = None
+        L.heroam_h5_reader_close.argtypes = [C.c_void_p]
+        L.heroam_h5_last_error.restype = C.c_char_p
+        L.free_records = C.CDLL(None).free
+        L.free_records.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -74,3 +91,67 @@ def write_particlefile(path: str, counts: np.ndarray, flat: np.ndarray, first_in
         arr[i].particle = flat.ctypes.data + int(off[i]) * PARTICLE_DTYPE.itemsize
     if not load_library().heroam_write_particlefile(path.encode(), arr, len(counts)):
         raise OSError(path)
+
+
+class TrajectoryFileWriter:
+    """``trajectory_%06d.h5`` in the reference's layout (h5file.c:69-112): one group
+    ``/Step_<k>`` per call, holding the dataset ``particles``."""
+
+    def __init__(self, path: str):
+        self._lib = load_library()
+        self._h = self._lib.heroam_h5_create(path.encode())
+        if not self._h:
+            raise OSError(self._lib.heroam_h5_last_error().decode())
+
+    def save_timestep(self, step: int, records: np.ndarray) -> None:
+        records = np.ascontiguousarray(records)
+        assert records.dtype == PARTICLE_DTYPE
+        if self._lib.heroam_h5_save_timestep(self._h, step, records.ctypes.data, len(records)) != 0:
+            raise OSError(self._lib.heroam_h5_last_error().decode())
+
+    def close(self) -> None:
+        if self._h:
+            h, self._h = self._h, None
+            if self._lib.heroam_h5_close(h) != 0:
+                raise OSError(self._lib.heroam_h5_last_error().decode())
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class TrajectoryFileReader:
+    """``open_file`` / ``read_timestep_from_hdf5`` of the reference (h5file.c:78-143)."""
+
+    def __init__(self, path: str):
+        self._lib = load_library()
+        self._h = self._lib.heroam_h5_open(path.encode())
+        if not self._h:
+            raise OSError(self._lib.heroam_h5_last_error().decode())
+
+    def num_steps(self) -> int:
+        return int(self._lib.heroam_h5_num_steps(self._h))
+
+    def read_timestep(self, step: int) -> np.ndarray:
+        out = ParticlesC()
+        if self._lib.heroam_h5_read_timestep(self._h, step, C.byref(out)) != 0:
+            raise KeyError(self._lib.heroam_h5_last_error().decode())
+        try:
+            n = int(out.no)
+            buf = C.string_at(out.particle, n * PARTICLE_DTYPE.itemsize)
+            return np.frombuffer(buf, dtype=PARTICLE_DTYPE).copy()
+        finally:
+            self._lib.free_records(out.particle)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.heroam_h5_reader_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
