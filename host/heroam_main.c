@@ -9,6 +9,8 @@
  *   #pragma omp parallel for simulate_...    heroam_gpu_simulate_batch, index blocks over GPUs
  *   particlefile_after_<N>                   heroam_write_particlefile
  *   free_particles                           heroam_gpu_free_particles
+ *   saveflag = 1: trajectory_%06d.h5         heroam_gpu_simulate_traced -> heroam_h5_save_timestep
+ *     (simulation.c:460-476, h5file.c)         (host/heroam_h5.c, no libhdf5 needed)
  *
  * Extra, optional environment knobs (the config file format is unchanged):
  *   HEROAM_MODE=exact|fast   arithmetic mode (default exact)
@@ -22,6 +24,7 @@
 #include <sys/types.h>
 
 #include "../include/heroam_gpu.h"
+#include "heroam_h5.h"
 #include "heroam_host.h"
 
 #ifdef _OPENMP
@@ -33,6 +36,59 @@ static int n_gpus_wanted(void) {
   const char *env = getenv("HEROAM_GPUS");
   if (env && atoi(env) > 0 && atoi(env) < have) have = atoi(env);
   return have;
+}
+
+/* saveflag = 1 (simulation.c:460-476, :522-523): every iteration of every trajectory goes to
+ * ./results/trajectory_%06d.h5 as /Step_<k>/particles.  Trajectories are traced in groups so
+ * that the number of files open at once stays bounded. */
+#define TRACE_GROUP 64
+typedef struct {
+  heroam_h5_writer *writer[TRACE_GROUP];
+} trace_files;
+
+static int trace_sink(void *user, uint32_t traj, uint32_t step, const heroam_particle *records, uint32_t no) {
+  trace_files *tf = (trace_files *)user;
+  return heroam_h5_save_timestep(tf->writer[traj], step, records, no);
+}
+
+static int simulate_traced_block(heroam_ctx *ctx, int helium_number, heroam_particles *block, int count) {
+  int failed = 0;
+  for (int g0 = 0; g0 < count && !failed; g0 += TRACE_GROUP) {
+    const int n = count - g0 < TRACE_GROUP ? count - g0 : TRACE_GROUP;
+    trace_files tf;
+    uint32_t counts[TRACE_GROUP];
+    size_t total = 0;
+    memset(&tf, 0, sizeof tf);
+    for (int i = 0; i < n; ++i) {
+      char name[100];
+      snprintf(name, sizeof name, "./results/trajectory_%06d.h5", (int)block[g0 + i].index); /* simulation.c:462 */
+      tf.writer[i] = heroam_h5_create(name);
+      if (!tf.writer[i]) {
+        fprintf(stderr, "%s\n", heroam_h5_last_error());
+        failed = 1;
+      }
+      counts[i] = block[g0 + i].no;
+      total += counts[i];
+    }
+    heroam_particle *flat = (heroam_particle *)malloc((total ? total : 1) * sizeof *flat);
+    size_t at = 0;
+    for (int i = 0; i < n; ++i) {
+      memcpy(flat + at, block[g0 + i].particle, counts[i] * sizeof *flat);
+      at += counts[i];
+    }
+    if (!failed && heroam_gpu_simulate_traced(ctx, (unsigned long long)helium_number, counts, flat, n, NULL, trace_sink, &tf)) {
+      fprintf(stderr, "%s\n", heroam_gpu_last_error());
+      failed = 1;
+    }
+    at = 0;
+    for (int i = 0; i < n; ++i) {
+      memcpy(block[g0 + i].particle, flat + at, counts[i] * sizeof *flat);
+      at += counts[i];
+      if (tf.writer[i] && heroam_h5_close(tf.writer[i])) failed = 1;
+    }
+    free(flat);
+  }
+  return failed;
 }
 
 static int simulate_for_number(int helium_number, const heroam_config *conf, const float *table,
@@ -60,7 +116,9 @@ static int simulate_for_number(int helium_number, const heroam_config *conf, con
 #pragma omp parallel for num_threads(n_gpus) schedule(static, 1) reduction(| : failed)
   for (int g = 0; g < n_gpus; ++g) {
     const long first = (long)g * number / n_gpus, last = (long)(g + 1) * number / n_gpus;
-    if (heroam_gpu_simulate_batch(ctx[g], (unsigned long long)helium_number, all + first, (int)(last - first), NULL)) {
+    if (conf->saveflag) {
+      failed |= simulate_traced_block(ctx[g], helium_number, all + first, (int)(last - first));
+    } else if (heroam_gpu_simulate_batch(ctx[g], (unsigned long long)helium_number, all + first, (int)(last - first), NULL)) {
       fprintf(stderr, "GPU %d: %s\n", g, heroam_gpu_last_error());
       failed |= 1;
     }
@@ -121,11 +179,6 @@ int main(int argc, char *argv[]) {
     return 1;
   }
   if (conf.print) heroam_print_config(stdout, &conf);
-  if (conf.saveflag) {
-    fprintf(stderr, "saveflag = 1 (per-step HDF5 trajectory dump, h5file.c) is not available in this build: "
-                    "libhdf5 is not installed; set saveflag = 0\n");
-    return 1;
-  }
   if (conf.force_grid_length <= 0) {
     fprintf(stderr, "force_grid_length must be positive\n");
     return 1;

@@ -19,6 +19,9 @@
  *                             simulation.c:438-526
  *   free_particles            simulation.h:85,         heroam_gpu_free_particles
  *                             simulation.c:339-341
+ *   saveflag = 1: save_timestep_to_hdf5 per iteration  heroam_gpu_simulate_traced
+ *                             simulation.c:460-476,      (+ host/heroam_h5.h for the file)
+ *                             h5file.c:88-112
  *   (none: the reference leaves histogramming to       heroam_gpu_run_stats
  *    the user of particlefile_after_<N>)
  */
@@ -155,6 +158,22 @@ int heroam_gpu_simulate_flat(heroam_ctx *ctx, unsigned long long he_number,
                              const uint32_t *counts, heroam_particle *flat, int count,
                              heroam_traj_result *results);
 
+/* The saveflag = 1 path of simulate_particles (simulation.c:460-476, :522-523): as
+ * heroam_gpu_simulate_flat, and in addition the sink is called once per trajectory and loop
+ * iteration with the records the reference hands to save_timestep_to_hdf5 at the top of that
+ * iteration (all `no` particles, frozen ones included) -- what ends up in
+ * ./results/trajectory_%06d.h5 as /Step_<step>/particles (h5file.c:88-112; host/heroam_h5.h
+ * writes that file).  Calls for one trajectory come in increasing step order; `trajectory` is
+ * the index within the batch; `records` is only valid during the call.  A non-zero return
+ * from the sink aborts the run.  The free-flight and splitting shortcuts are off on this
+ * path (every record must be current at every step), so it runs at the speed of the I/O it
+ * feeds, not of the histogram path. */
+typedef int (*heroam_step_sink)(void *user, uint32_t trajectory, uint32_t step,
+                                const heroam_particle *records, uint32_t no);
+int heroam_gpu_simulate_traced(heroam_ctx *ctx, unsigned long long he_number,
+                               const uint32_t *counts, heroam_particle *flat, int count,
+                               heroam_traj_result *results, heroam_step_sink sink, void *user);
+
 /* The same work split in three so that a benchmark can time the resident part:
  * upload copies the batch to the device, run integrates it there (may be called
  * once per upload), download copies the final states (and results) back. */
@@ -189,6 +208,9 @@ int heroam_gpu_last_run_info(const heroam_ctx *ctx, heroam_run_info *out);
 /* Register-resident FFMA microbenchmark on the context's device: the measured FP32
  * peak used as the roofline denominator.  TFLOP/s. */
 int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_clock_mhz);
+/* The same with both the multiplier and the addend in registers (three register operands per
+ * FFMA, as in the integrate kernels) instead of the constant bank. */
+int heroam_gpu_fp32_peak_rrr(heroam_ctx *ctx, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,9 @@ class RefOracle:
         L.ref_simulate.argtypes = [C.c_ulonglong, C.POINTER(Config), _fp, C.c_int, _u32p, C.c_void_p, C.c_int, C.c_int]
         L.ref_calculate_force.restype = None
         L.ref_calculate_force.argtypes = [C.c_uint, C.c_void_p, C.POINTER(Config), _fp]
+        if hasattr(L, "ref_simulate_traced"):
+            L.ref_simulate_traced.restype = C.c_ulong
+            L.ref_simulate_traced.argtypes = [C.c_ulonglong, C.POINTER(Config), _fp, C.c_uint, C.c_void_p, C.c_ulong, C.c_void_p]
         L.ref_find_success.restype = C.c_int
         L.ref_find_success.argtypes = [C.c_uint, C.c_void_p]
         L.ref_find_accelration.restype = None
@@ -149,6 +152,17 @@ class RefOracle:
         self.lib.ref_simulate(he_number, C.byref(conf), _ptr(table, _fp), len(counts), _ptr(counts, _u32p),
                               out.ctypes.data, nthreads, 1 if dynamic else 0)
         return out
+
+    def simulate_traced(self, conf: Config, he_number: int, table: np.ndarray, particles: np.ndarray, cap_steps: int):
+        """One trajectory with saveflag=1: (snapshots[steps, no], final records).  The snapshots are
+        what the reference hands to save_timestep_to_hdf5 at the top of every loop iteration."""
+        final = np.ascontiguousarray(particles.copy())
+        snaps = np.zeros((cap_steps, len(final)), dtype=PARTICLE_DTYPE)
+        n = int(self.lib.ref_simulate_traced(he_number, C.byref(conf), _ptr(table, _fp), len(final), final.ctypes.data,
+                                             cap_steps, snaps.ctypes.data))
+        if n > cap_steps:
+            raise ValueError(f"{n} steps, buffer holds {cap_steps}")
+        return snaps[:n].copy(), final
 
     def calculate_force(self, conf: Config, table: np.ndarray, particles: np.ndarray) -> np.ndarray:
         out = np.ascontiguousarray(particles.copy())

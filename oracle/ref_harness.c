@@ -11,7 +11,9 @@
  *
  * The three HDF5 entry points the trajectory loop calls when saveflag=1
  * (reference simulation.c:463,:476,:523) are defined here as no-ops: libhdf5
- * does not exist in this image and the harness always runs with saveflag=0.
+ * does not exist in this image.  They are defined here: no-ops when saveflag=0, and with
+ * saveflag=1 (ref_simulate_traced) save_timestep_to_hdf5 copies what it is given into a
+ * caller-supplied buffer, which is how the per-step golden states are obtained.
  *
  * Everything exported is prefixed ref_ and uses flat arrays so that Python
  * (ctypes, tests/ only) and bench.py's cpu_baseline leg can drive it.
@@ -31,11 +33,25 @@
 #include REF_SIMULATION_C
 
 /* ---- HDF5 no-ops (declared in the reference's h5file.h) ---- */
+/* When a capture buffer is armed (ref_simulate_traced below) save_timestep_to_hdf5 -- called by
+ * the reference itself at the top of every loop iteration when saveflag=1, simulation.c:475-476
+ * -- appends the records it is handed: exactly what the reference would put into
+ * /Step_<step>/particles. */
+static _Thread_local Particle *g_trace_out = NULL;
+static _Thread_local unsigned long g_trace_cap = 0, g_trace_steps = 0;
 hid_t initialize_file(const char *filename) { (void)filename; return 0; }
 hid_t open_file(const char *filename) { (void)filename; return 0; }
 herr_t save_timestep_to_hdf5(const hid_t file_id, const unsigned int step,
                              const Particles *particles) {
-  (void)file_id; (void)step; (void)particles; return 0;
+  (void)file_id;
+  if (g_trace_out) {
+    if (step != g_trace_steps) return -1; /* the reference numbers the groups 0, 1, 2, ... */
+    if (g_trace_steps < g_trace_cap)
+      memcpy(g_trace_out + (size_t)g_trace_steps * particles->no, particles->particle,
+             (size_t)particles->no * sizeof(Particle));
+    g_trace_steps++;
+  }
+  return 0;
 }
 herr_t read_timestep_from_hdf5(const hid_t file_id, const unsigned int step,
                                Particles *particles) {
@@ -160,6 +176,26 @@ void ref_simulate(unsigned long long he_number, const struct config *conf,
       simulate_particles(conf, he_number, force_list, all + i);
   }
   free(all);
+}
+
+/* ---- one trajectory with saveflag=1: every state the reference would write to its HDF5 file.
+ * out receives up to cap_steps snapshots of `no` records each; returns the number of
+ * save_timestep_to_hdf5 calls (= loop iterations).  `p` is advanced in place. */
+unsigned long ref_simulate_traced(unsigned long long he_number, const struct config *conf,
+                                  const float *force_list, unsigned int no, Particle *p,
+                                  unsigned long cap_steps, Particle *out) {
+  struct config c = *conf;
+  c.saveflag = 1;
+  Particles ps;
+  ps.no = no;
+  ps.index = 0;
+  ps.particle = p;
+  g_trace_out = out;
+  g_trace_cap = cap_steps;
+  g_trace_steps = 0;
+  simulate_particles(&c, he_number, force_list, &ps);
+  g_trace_out = NULL;
+  return g_trace_steps;
 }
 
 /* ---- known-answer wrappers for the file-static helpers ---- */

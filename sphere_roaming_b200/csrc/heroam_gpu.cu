@@ -40,6 +40,14 @@ struct DevBuf {
   cudaError_t alloc(size_t count) { return cudaMalloc(&ptr, count * sizeof(T)); }
 };
 
+// page-locked host memory with the same lifetime rule
+template <class T>
+struct PinnedBuf {
+  T *ptr = nullptr;
+  ~PinnedBuf() { if (ptr) cudaFreeHost(ptr); }
+  cudaError_t alloc(size_t count) { return cudaMallocHost(&ptr, count * sizeof(T)); }
+};
+
 // ---------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------
@@ -588,6 +596,187 @@ extern "C" int heroam_gpu_simulate_batch(heroam_ctx *ctx, unsigned long long he_
   return HEROAM_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// Per-step capture (saveflag = 1, simulation.c:460-476, :522-523).  The batch advances in
+// chunks of `chunk` loop iterations; k_integrate_capture leaves the snapshots of a chunk in a
+// device buffer, which is copied to page-locked host memory on a second stream and handed to
+// the sink while the next chunk is being integrated (two buffers).
+// ---------------------------------------------------------------------------------
+struct CaptureBuffers {
+  DevBuf<heroam_particle> d_snap[2];
+  DevBuf<uint32_t> d_taken[2], d_from[2];
+  PinnedBuf<heroam_particle> h_snap[2];
+  PinnedBuf<uint32_t> h_taken[2], h_from[2];
+  cudaStream_t copy = nullptr;
+  cudaEvent_t filled[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  ~CaptureBuffers() {
+    for (int i = 0; i < 2; ++i) {
+      if (filled[i]) cudaEventDestroy(filled[i]);
+      if (copied[i]) cudaEventDestroy(copied[i]);
+    }
+    if (copy) cudaStreamDestroy(copy);
+  }
+};
+
+static int deliver_chunk(const heroam_ctx *ctx, const uint32_t *counts, const std::vector<uint32_t> &first, uint32_t chunk,
+                         const heroam_particle *snap, const uint32_t *taken, const uint32_t *from,
+                         std::vector<uint32_t> &next_step, heroam_step_sink sink, void *user) {
+  for (uint32_t t = 0; t < ctx->n_traj; ++t) {
+    if (!taken[t]) continue;
+    if (from[t] != next_step[t])
+      return fail(HEROAM_E_CUDA, "capture: trajectory %u resumed at step %u, expected %u", t, from[t], next_step[t]);
+    const heroam_particle *rec = snap + (size_t)first[t] * chunk;
+    for (uint32_t i = 0; i < taken[t]; ++i)
+      if (sink(user, t, from[t] + i, rec + (size_t)i * counts[t], counts[t]))
+        return fail(HEROAM_E_ARG, "capture: the sink refused step %u of trajectory %u", from[t] + i, t);
+    next_step[t] += taken[t];
+  }
+  return HEROAM_OK;
+}
+
+template <class R, class H>
+static int run_traced(heroam_ctx *ctx, const Consts &c, const uint32_t *counts, const std::vector<uint32_t> &first,
+                      std::vector<uint32_t> &next_step, heroam_step_sink sink, void *user) {
+  DevView v = make_view(ctx, c);
+  const uint32_t n = ctx->n_traj;
+  const unsigned tgrid = (n + 127) / 128;
+  const uint32_t cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu
+                                                                                    : (uint32_t)ctx->opt.max_steps;
+  // snapshots of one chunk: n_particles * chunk records, at most 256 MB per buffer
+  uint32_t chunk = 4096;
+  while (chunk > 1 && (size_t)ctx->n_particles * chunk * sizeof(heroam_particle) > (256ull << 20)) chunk /= 2;
+  if (ctx->opt.segment_steps && ctx->opt.segment_steps < chunk) chunk = ctx->opt.segment_steps;
+  const size_t snap_records = (size_t)ctx->n_particles * chunk;
+  CaptureBuffers cb;
+  CU(cudaStreamCreateWithFlags(&cb.copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CU(cb.d_snap[i].alloc(snap_records));
+    CU(cb.d_taken[i].alloc(n));
+    CU(cb.d_from[i].alloc(n));
+    CU(cb.h_snap[i].alloc(snap_records));
+    CU(cb.h_taken[i].alloc(n));
+    CU(cb.h_from[i].alloc(n));
+    CU(cudaEventCreateWithFlags(&cb.filled[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&cb.copied[i], cudaEventDisableTiming));
+  }
+  CU(cudaEventRecord(ctx->ev_start, ctx->main));
+  CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
+  k_prepare<<<tgrid, 128, 0, ctx->main>>>(v, ctx->d_first, ctx->d_counts);
+  CU(cudaGetLastError());
+  ctx->info.kernel_launches++;
+  const Segments sg = make_capture_segments(chunk);
+  int cur = 0;
+  bool pending = false;  // buffer cur ^ 1 is on its way to the host
+  int rc = HEROAM_OK;
+  for (;;) {
+    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
+    k_resolve_and_bin<R><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
+    CU(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaStreamSynchronize(ctx->main));
+    uint64_t live = 0;
+    for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
+    if (live) {
+      ctx->info.passes++;
+      CaptureView cv;
+      cv.snap = cb.d_snap[cur].ptr;
+      cv.taken = cb.d_taken[cur].ptr;
+      cv.from_step = cb.d_from[cur].ptr;
+      cv.chunk = chunk;
+      CU(cudaMemsetAsync(cv.taken, 0, (size_t)n * sizeof(uint32_t), ctx->main));
+      for (int b = 1; b < BIN_FREE; ++b) {
+        const uint32_t cnt = ctx->h_bin_count[b];
+        if (!cnt) continue;
+        k_integrate_capture<H><<<(cnt + 63) / 64, 64, 0, ctx->main>>>(v, cv, ctx->d_bin_list + (size_t)b * n, cnt);
+        CU(cudaGetLastError());
+        ctx->info.kernel_launches++;
+      }
+      CU(cudaEventRecord(cb.filled[cur], ctx->main));
+      CU(cudaStreamWaitEvent(cb.copy, cb.filled[cur], 0));
+      CU(cudaMemcpyAsync(cb.h_snap[cur].ptr, cv.snap, snap_records * sizeof(heroam_particle), cudaMemcpyDeviceToHost, cb.copy));
+      CU(cudaMemcpyAsync(cb.h_taken[cur].ptr, cv.taken, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, cb.copy));
+      CU(cudaMemcpyAsync(cb.h_from[cur].ptr, cv.from_step, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, cb.copy));
+      CU(cudaEventRecord(cb.copied[cur], cb.copy));
+      ctx->info.d2h_bytes += snap_records * sizeof(heroam_particle) + 2ull * n * sizeof(uint32_t);
+    }
+    if (pending) {  // hand the previous chunk to the sink while this one is integrated
+      const int prev = cur ^ 1;
+      CU(cudaEventSynchronize(cb.copied[prev]));
+      rc = deliver_chunk(ctx, counts, first, chunk, cb.h_snap[prev].ptr, cb.h_taken[prev].ptr, cb.h_from[prev].ptr,
+                         next_step, sink, user);
+      pending = false;
+      if (rc) break;
+    }
+    if (!live) break;
+    pending = true;
+    cur ^= 1;
+  }
+  CU(cudaStreamSynchronize(cb.copy));
+  CU(cudaStreamSynchronize(ctx->main));
+  if (rc) return rc;
+  k_results<<<tgrid, 128, 0, ctx->main>>>(v, ctx->d_results);
+  CU(cudaGetLastError());
+  ctx->info.kernel_launches++;
+  CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->main));
+  CU(cudaEventRecord(ctx->ev_stop, ctx->main));
+  CU(cudaStreamSynchronize(ctx->main));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+  ctx->info.device_ms = ms;
+  ctx->info.particle_steps = ctx->h_counters->particle_steps;
+  ctx->info.pair_steps = ctx->h_counters->pair_steps;
+  ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
+  ctx->info.trajectories = n;
+  ctx->info.particles = ctx->n_particles;
+  if (ctx->h_counters->unsupported)
+    return fail(HEROAM_E_UNSUPPORTED, "%llu trajectories have more than %d moving particles", ctx->h_counters->unsupported,
+                MAX_ACTIVE);
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_simulate_traced(heroam_ctx *ctx, unsigned long long he_number, const uint32_t *counts,
+                                          heroam_particle *flat, int count, heroam_traj_result *results,
+                                          heroam_step_sink sink, void *user) {
+  if (!sink) return fail(HEROAM_E_ARG, "heroam_gpu_simulate_traced: null sink");
+  int rc = heroam_gpu_upload(ctx, he_number, counts, flat, count);
+  if (rc) return rc;
+  ctx->uploaded = false;
+  if (count == 0) return HEROAM_OK;
+  Consts c;
+  rc = make_consts(ctx->conf, he_number, &c);
+  if (rc) return rc;
+  std::vector<uint32_t> first((size_t)count), next_step((size_t)count, 0u);
+  size_t total = 0;
+  for (int i = 0; i < count; ++i) {
+    first[i] = (uint32_t)total;
+    total += counts[i];
+  }
+  rc = ctx->opt.mode == HEROAM_MODE_EXACT ? run_traced<Exact, Exact>(ctx, c, counts, first, next_step, sink, user)
+                                          : run_traced<Fast, Fast>(ctx, c, counts, first, next_step, sink, user);
+  if (rc) return rc;
+  std::vector<heroam_traj_result> res((size_t)count);
+  rc = heroam_gpu_download(ctx, flat, res.data());
+  if (rc) return rc;
+  // A trajectory nobody can move in (every particle frozen at import) still runs one iteration of the
+  // reference's loop (Q2): its only snapshot is the state it was imported in, which that
+  // iteration leaves unchanged.
+  size_t at = 0;
+  for (int i = 0; i < count; ++i) {
+    if (next_step[i] == 0 && res[i].steps == 1) {
+      if (sink(user, (uint32_t)i, 0u, flat + at, counts[i]))
+        return fail(HEROAM_E_ARG, "capture: the sink refused step 0 of trajectory %d", i);
+      next_step[i] = 1;
+    }
+    if (next_step[i] != res[i].steps)
+      return fail(HEROAM_E_CUDA, "capture: trajectory %d ran %u iterations but %u snapshots were taken", i, res[i].steps,
+                  next_step[i]);
+    at += counts[i];
+  }
+  if (results) memcpy(results, res.data(), (size_t)count * sizeof(heroam_traj_result));
+  return HEROAM_OK;
+}
+
 extern "C" int heroam_gpu_last_run_info(const heroam_ctx *ctx, heroam_run_info *out) {
   if (!ctx || !out) return fail(HEROAM_E_ARG, "null argument");
   *out = ctx->info;
@@ -627,6 +816,32 @@ extern "C" int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
     *sm_clock_mhz = khz / 1000.0;
   }
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_fp32_peak_rrr(heroam_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return fail(HEROAM_E_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  DevBuf<float> out_buf, coef_buf;
+  CU(out_buf.alloc(1));
+  CU(coef_buf.alloc(8));
+  const float coef[8] = {0.999f, 0.998f, 0.997f, 0.996f, 0.001f, 0.002f, 0.003f, 0.004f};
+  CU(cudaMemcpy(coef_buf.ptr, coef, sizeof coef, cudaMemcpyHostToDevice));
+  const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(ctx->ev_c0, ctx->main));
+    k_fma_peak_rrr<<<blocks, threads, 0, ctx->main>>>(out_buf.ptr, coef_buf.ptr, iters);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_c1, ctx->main));
+    CU(cudaStreamSynchronize(ctx->main));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev_c0, ctx->ev_c1));
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  *tflops = best;
   return HEROAM_OK;
 }
 

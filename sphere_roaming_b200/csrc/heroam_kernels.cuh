@@ -268,6 +268,8 @@ struct Segments {
   uint32_t free_stride;   // entries reserved per whole-trajectory free-flight tier in the free list
   uint32_t drain;         // 1 while the run is draining (few live trajectories, latency bound):
                           // the short free-flight tier would only slow per-pass progress
+  uint32_t no_flight;     // 1: per-step capture -- every particle's record must be current at every step
+                          // boundary, so nobody flies and nothing is split off
 };
 
 __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split_window_max) {
@@ -308,6 +310,17 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
   for (int a = 0; a <= THREAD_MAX_A; ++a) sg.of_bin[BIN_CORE + a] = window;
   sg.free_stride = 0;
   sg.drain = drain ? 1u : 0u;
+  sg.no_flight = 0;
+  return sg;
+}
+
+// per-step capture: every bin advances by the same number of steps (one chunk of snapshots)
+__host__ inline Segments make_capture_segments(uint32_t chunk) {
+  Segments sg;
+  for (int b = 0; b < N_BINS; ++b) sg.of_bin[b] = chunk;
+  sg.free_stride = 0;
+  sg.drain = 0;
+  sg.no_flight = 1;
   return sg;
 }
 
@@ -574,6 +587,11 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
     if (stop > step_cap) stop = step_cap;
     return stop;
   };
+  if (sg.no_flight) {
+    out.bin = bin_of(a);
+    m.step_stop = clip(m.steps + sg.of_bin[out.bin]);
+    return out;
+  }
   // (1) the whole trajectory in free flight: the longest fixed-length tier its horizon covers
   const uint32_t horizon = free_flight_horizon(v, m);
   for (int tier = 2; tier >= (sg.drain ? 1 : 0); --tier)
@@ -1363,6 +1381,107 @@ __global__ void k_integrate_records(DevView v, const uint32_t *__restrict__ list
 }
 
 // ---------------------------------------------------------------------------------
+// k_integrate_capture: the saveflag = 1 path (simulation.c:460-476).  One thread per
+// trajectory, state in the global records exactly as k_integrate_records keeps it (every
+// field of every record is the reference's at each step boundary); at the top of every loop
+// iteration all `no` records of the trajectory -- frozen ones included -- are copied to the
+// snapshot buffer, which is what the reference hands to save_timestep_to_hdf5 there.
+// Snapshot i of trajectory t in this pass lives at snap[(first * chunk) + i * no .. + no).
+// ---------------------------------------------------------------------------------
+struct CaptureView {
+  heroam_particle *snap;   // n_particles * chunk records
+  uint32_t *taken;         // [t] snapshots written in this pass
+  uint32_t *from_step;     // [t] loop iteration of the first of them
+  uint32_t chunk;
+};
+
+template <class P>
+__global__ void k_integrate_capture(DevView v, CaptureView cap, const uint32_t *__restrict__ list, uint32_t count) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= count) return;
+  const Consts &c = v.c;
+  const uint32_t t = list[item];
+  TrajMeta m = v.meta[t];
+  heroam_particle *base = v.particles + m.first;
+  const uint32_t *act = v.act + m.first;
+  const uint32_t a = m.n_active;
+  heroam_particle *snap = cap.snap + (size_t)m.first * cap.chunk;
+  uint32_t taken = 0;
+  cap.from_step[t] = m.steps;
+  unsigned long long done_steps = 0, inrange_total = 0;
+  while (m.steps < m.step_stop && taken < cap.chunk) {
+    {  // the state at the top of iteration m.steps
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(base);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(snap + (size_t)taken * m.no);
+      const uint32_t words = m.no * (uint32_t)(sizeof(heroam_particle) / sizeof(uint32_t));
+      for (uint32_t i = 0; i < words; ++i) dst[i] = src[i];
+      ++taken;
+    }
+    for (uint32_t s = 0; s < a; ++s) {
+      heroam_particle *p = base + act[s];
+      float hk[3], wh[3], q[4], r[3];
+      half_kick<P>(c, p->position, p->force, hk);
+      wh[0] = P::add(p->ang_velocity[0], hk[0]);
+      wh[1] = P::add(p->ang_velocity[1], hk[1]);
+      wh[2] = P::add(p->ang_velocity[2], hk[2]);
+      q[0] = p->orientation[0]; q[1] = p->orientation[1]; q[2] = p->orientation[2]; q[3] = p->orientation[3];
+      drift<P>(c, wh, q, r);
+      p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
+      st3(p->position, r);
+      st3(p->force, wh);  // scratch slot: w(t + dt/2)
+    }
+    bool met = false;
+    for (uint32_t js = 0; js < a && !met; ++js)
+      for (uint32_t ks = js + 1; ks < a; ++ks)
+        if (pair_dist_sq<P>(base[act[js]].position, base[act[ks]].position) < c.icd2) { met = true; break; }
+    if (met) { m.status = ST_MIDSTEP; break; }  // the resolve kernel finishes this iteration
+    for (uint32_t s = 0; s < a; ++s) {
+      heroam_particle *p = base + act[s];
+      st3(p->velocity, p->force);  // keep w(t + dt/2) while the forces are rebuilt
+      p->force[0] = 0.0f; p->force[1] = 0.0f; p->force[2] = 0.0f;
+    }
+    uint32_t in_step = 0;
+    for (uint32_t js = 0; js + 1 < a; ++js) {
+      heroam_particle *pj = base + act[js];
+      for (uint32_t ks = js + 1; ks < a; ++ks) {
+        heroam_particle *pk = base + act[ks];
+        float fj[3], fk[3];
+        ld3(pj->force, fj);
+        ld3(pk->force, fk);
+        pair_force<P>(c, v.table, pj->position, pk->position, fj, fk, in_step);
+        st3(pj->force, fj);
+        st3(pk->force, fk);
+      }
+    }
+    m.time = __fadd_rn(m.time, c.dt);
+    for (uint32_t s = 0; s < a; ++s) {
+      heroam_particle *p = base + act[s];
+      float hk[3], w[3], vel[3], v2;
+      half_kick<P>(c, p->position, p->force, hk);
+      w[0] = P::add(p->velocity[0], hk[0]);
+      w[1] = P::add(p->velocity[1], hk[1]);
+      w[2] = P::add(p->velocity[2], hk[2]);
+      st3(p->ang_velocity, w);
+      stored_velocity<P>(p->position, w, vel, v2);
+      st3(p->velocity, vel);
+      p->velocity_sq = v2;
+      p->time = m.time;
+      p->force_mag = (act[s] + 1u < m.no) ? vec_norm(p->force) : 0.0f;
+    }
+    ++m.steps;
+    ++done_steps;
+    inrange_total += in_step;
+  }
+  cap.taken[t] = taken;
+  v.meta[t] = m;
+  if (done_steps) {
+    atomicAdd(&v.counters->particle_steps, done_steps * a);
+    atomicAdd(&v.counters->pair_steps, done_steps * ((unsigned long long)a * (a - 1) / 2));
+    atomicAdd(&v.counters->inrange_steps, inrange_total);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // k_results: per-trajectory outcome for the host
 // ---------------------------------------------------------------------------------
 __global__ void k_results(DevView v, heroam_traj_result *__restrict__ out) {
@@ -1398,6 +1517,22 @@ __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a
   }
   const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
   if (s == 12345.678f) out[0] = s;  // never true in practice; keeps the chains alive
+}
+
+// The same with three REGISTER operands per FFMA (multiplier and addend come from memory, not
+// from the constant bank): the form almost every FFMA of the integrate kernels has.
+__global__ void __launch_bounds__(256) k_fma_peak_rrr(float *out, const float *__restrict__ coef, int iters) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  const float a0 = coef[0], a1 = coef[1], a2 = coef[2], a3 = coef[3], b0 = coef[4], b1 = coef[5], b2 = coef[6], b3 = coef[7];
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a0, b0); x1 = fmaf(x1, a1, b1); x2 = fmaf(x2, a2, b2); x3 = fmaf(x3, a3, b3);
+      x4 = fmaf(x4, a0, b1); x5 = fmaf(x5, a1, b2); x6 = fmaf(x6, a2, b3); x7 = fmaf(x7, a3, b0);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678f) out[0] = s;
 }
 
 }  // namespace heroam

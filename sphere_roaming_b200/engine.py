@@ -38,6 +38,7 @@ ABI_SYMBOLS = (
     "heroam_gpu_set_mode",
     "heroam_gpu_simulate_batch",
     "heroam_gpu_simulate_flat",
+    "heroam_gpu_simulate_traced",
     "heroam_gpu_upload",
     "heroam_gpu_run",
     "heroam_gpu_download",
@@ -47,6 +48,7 @@ ABI_SYMBOLS = (
     "heroam_gpu_run_stats",
     "heroam_gpu_last_run_info",
     "heroam_gpu_fp32_peak",
+    "heroam_gpu_fp32_peak_rrr",
 )
 
 
@@ -103,6 +105,9 @@ class Stats(C.Structure):
     ]
 
 
+#: heroam_step_sink of include/heroam_gpu.h
+STEP_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32)
+
 _lib = None
 
 
@@ -131,6 +136,8 @@ def load_library() -> C.CDLL:
     L.heroam_gpu_simulate_batch.argtypes = [vp, C.c_ulonglong, C.POINTER(ParticlesC), C.c_int, vp]
     L.heroam_gpu_simulate_flat.restype = C.c_int
     L.heroam_gpu_simulate_flat.argtypes = [vp, C.c_ulonglong, u32p, vp, C.c_int, vp]
+    L.heroam_gpu_simulate_traced.restype = C.c_int
+    L.heroam_gpu_simulate_traced.argtypes = [vp, C.c_ulonglong, u32p, vp, C.c_int, vp, STEP_SINK, vp]
     L.heroam_gpu_upload.restype = C.c_int
     L.heroam_gpu_upload.argtypes = [vp, C.c_ulonglong, u32p, vp, C.c_int]
     L.heroam_gpu_run.restype = C.c_int
@@ -149,6 +156,8 @@ def load_library() -> C.CDLL:
     L.heroam_gpu_last_run_info.argtypes = [vp, C.POINTER(RunInfo)]
     L.heroam_gpu_fp32_peak.restype = C.c_int
     L.heroam_gpu_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.heroam_gpu_fp32_peak_rrr.restype = C.c_int
+    L.heroam_gpu_fp32_peak_rrr.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -214,6 +223,33 @@ class Engine:
         res = np.zeros(len(counts), dtype=RESULT_DTYPE)
         self._check(self.lib.heroam_gpu_simulate_flat(self.handle, he_number, counts.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                       out.ctypes.data, len(counts), res.ctypes.data))
+        return out, res
+
+    def simulate_traced(self, he_number: int, counts: np.ndarray, flat: np.ndarray, sink):
+        """``heroam_gpu_simulate_traced`` (the reference's saveflag = 1): ``sink(trajectory, step,
+        records)`` receives a copy of the records the reference would write to
+        ``/Step_<step>/particles`` of that trajectory's file.  Returns (final records, results)."""
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        out = np.ascontiguousarray(flat.copy())
+        assert out.dtype == PARTICLE_DTYPE and int(counts.sum()) == len(out)
+        res = np.zeros(len(counts), dtype=RESULT_DTYPE)
+        failure = []
+
+        def _sink(_user, traj, step, records, no):
+            try:
+                buf = C.string_at(records, no * PARTICLE_DTYPE.itemsize)
+                sink(int(traj), int(step), np.frombuffer(buf, dtype=PARTICLE_DTYPE))
+                return 0
+            except Exception as exc:  # propagate after the C call has unwound
+                failure.append(exc)
+                return 1
+
+        cb = STEP_SINK(_sink)
+        rc = self.lib.heroam_gpu_simulate_traced(self.handle, he_number, counts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                 out.ctypes.data, len(counts), res.ctypes.data, cb, None)
+        if failure:
+            raise failure[0]
+        self._check(rc)
         return out, res
 
     def simulate_inplace(self, he_number: int, counts: np.ndarray, flat: np.ndarray, results: np.ndarray) -> None:
@@ -293,3 +329,8 @@ class Engine:
         tf, mhz = C.c_double(0), C.c_double(0)
         self._check(self.lib.heroam_gpu_fp32_peak(self.handle, C.byref(tf), C.byref(mhz)))
         return tf.value, mhz.value
+
+    def fp32_peak_rrr(self) -> float:
+        tf = C.c_double(0)
+        self._check(self.lib.heroam_gpu_fp32_peak_rrr(self.handle, C.byref(tf)))
+        return tf.value
