@@ -203,6 +203,24 @@ int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number,
                          unsigned long long first_index, unsigned long long count,
                          heroam_stats *out);
 
+/* A laser sweep (BASELINE config 4: intensity x pulse width at one droplet size) as ONE run of
+ * the streaming pool: the points' trajectories are concatenated into one index space, so the
+ * drain of one point (its few trajectories that run to max_time) overlaps the bulk of the
+ * next ones instead of idling the GPU once per point.  Point p uses conf with intensity and
+ * pulse_width replaced (they only enter the mean excitation number, simulation.c:289-293) and
+ * the Philox indices [first_index, first_index + count): out[p] is exactly what
+ * heroam_gpu_run_stats would return for that point alone, except out[p].info, which describes
+ * the whole sweep.  At most 32 points per call.  (The reference's own sweep, over droplet
+ * sizes, main.c:158-164, changes the sphere radius and stays a loop of runs.) */
+typedef struct heroam_sweep_point {
+  float intensity;                /* [GW/cm^2] */
+  float pulse_width;              /* [fs]      */
+  unsigned long long first_index; /* first Philox trajectory index of this point (sharding) */
+  unsigned long long count;       /* trajectories of this point on this GPU */
+} heroam_sweep_point;
+int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_number, int n_points,
+                         const heroam_sweep_point *points, heroam_stats *out /* [n_points] */);
+
 int heroam_gpu_last_run_info(const heroam_ctx *ctx, heroam_run_info *out);
 
 /* Register-resident FFMA microbenchmark on the context's device: the measured FP32

@@ -37,7 +37,7 @@ enum : uint32_t {
   ST_DONE = 16     // ST_DONE + HEROAM_DONE_* once finished
 };
 
-struct TrajMeta {      // 56 bytes per trajectory
+struct TrajMeta {      // 60 bytes per trajectory
   uint32_t first;      // first record of this trajectory in the flat particle array
   uint32_t no;         // particles in the trajectory
   uint32_t steps;      // completed iterations of the step loop (of the core, see below)
@@ -54,6 +54,7 @@ struct TrajMeta {      // 56 bytes per trajectory
   float loner_time0;     // the clock at loner_from
   uint32_t cross_from;   // core step up to which core-loner / loner-loner pair-steps are accounted
   uint32_t core_slots;   // act[first .. first+core_slots) = core, then n_loners loner entries
+  uint32_t point;        // sweep point the trajectory belongs to (streaming pool; 0 otherwise)
 };
 
 // Loop-invariant scalars, rounded on the host exactly where the reference rounds them.

@@ -136,6 +136,7 @@ __global__ void k_prepare(DevView v, const uint32_t *__restrict__ first,
   m.status = ST_LIVE;
   m.step_stop = 0;
   m.n_loners = 0; m.loner_from = 0; m.loner_until = 0; m.loner_time0 = 0.0f; m.cross_from = 0; m.core_slots = m.n_active;
+  m.point = 0;
   v.meta[t] = m;
 }
 

@@ -279,12 +279,23 @@ __global__ void k_stats(DevView v, DevStats *__restrict__ st) {
 // ---------------------------------------------------------------------------------
 constexpr uint32_t ST_FREE = 0xfffffff0u;
 
+// A run of the pool covers one or more SWEEP POINTS (laser settings: different mean excitation
+// numbers on the same droplet).  The points share one index space -- point 0's trajectories,
+// then point 1's, ... -- so that one point's drain overlaps the next points' bulk; each point
+// keeps its own Philox indices (first_index + i, exactly as if it were run on its own) and its
+// own histogram block.
+constexpr int MAX_SWEEP_POINTS = 32;
+
 struct PoolParams {
-  SampleParams sp;
-  unsigned long long *cursor;   // next trajectory index (relative to sp.first_index)
-  unsigned long long count;     // trajectories in the run
+  SampleParams sp;              // sp.limit / sp.first_index are per point, see below
+  unsigned long long *cursor;   // next position in the concatenated index space
+  unsigned long long count;     // trajectories in the run, all points together
   uint32_t cap;                 // records per slot
-  DevStats *stats;
+  uint32_t n_points;
+  DevStats *stats;              // n_points blocks
+  unsigned long long point_end[MAX_SWEEP_POINTS];    // exclusive end of each point in the index space
+  unsigned long long point_first[MAX_SWEEP_POINTS];  // its first Philox trajectory index
+  double point_limit[MAX_SWEEP_POINTS];              // its exp(-lambda)
 };
 
 __global__ void k_pool_init(DevView v, uint32_t cap) {
@@ -294,6 +305,7 @@ __global__ void k_pool_init(DevView v, uint32_t cap) {
   m.first = t * cap;
   m.no = 0; m.steps = 0; m.time = 0.0f; m.n_flagged = 0; m.n_active = 0; m.step_stop = 0;
   m.n_loners = 0; m.loner_from = 0; m.loner_until = 0; m.loner_time0 = 0.0f; m.cross_from = 0; m.core_slots = 0;
+  m.point = 0;
   m.status = ST_FREE;
   v.meta[t] = m;
 }
@@ -314,14 +326,18 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
         if (m.status < ST_DONE) break;  // still live: scheduled
       }
       if (m.status != ST_FREE) {
-        accumulate_stats(v, m, pool.stats);
+        accumulate_stats(v, m, pool.stats + m.point);
         m.status = ST_FREE;
       }
       const unsigned long long idx = atomicAdd(pool.cursor, 1ull);
       if (idx >= pool.count) break;
+      uint32_t pt = 0;
+      while (pt + 1u < pool.n_points && idx >= pool.point_end[pt]) ++pt;
+      const unsigned long long local = idx - (pt ? pool.point_end[pt - 1u] : 0ull);
       Philox g;
-      g.begin(pool.sp.seed, pool.sp.he_number, pool.sp.first_index + idx);
-      const uint32_t n = sample_count(g, pool.sp.limit);
+      g.begin(pool.sp.seed, pool.sp.he_number, pool.point_first[pt] + local);
+      const uint32_t n = sample_count(g, pool.point_limit[pt]);
+      m.point = pt;
       m.no = n; m.steps = 0; m.time = 0.0f; m.n_flagged = 0; m.step_stop = 0;
       m.n_loners = 0; m.loner_from = 0; m.loner_until = 0; m.loner_time0 = 0.0f; m.cross_from = 0; m.core_slots = 0;
       if (n > pool.cap) {  // does not fit a slot: counted, not integrated
@@ -527,22 +543,42 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
   return HEROAM_OK;
 }
 
-extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index,
-                                    unsigned long long count, heroam_stats *out) {
-  if (!ctx || !out) return fail(HEROAM_E_ARG, "heroam_gpu_run_stats: null argument");
+static double point_lambda(const heroam_config &conf, unsigned long long he_number, float intensity, float pulse_width) {
+  heroam_config c = conf;
+  c.intensity = intensity;
+  c.pulse_width = pulse_width;
+  return host_lambda(c, he_number);
+}
+
+extern "C" int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_number, int n_points,
+                                    const heroam_sweep_point *points, heroam_stats *out) {
+  if (!ctx || !out || !points) return fail(HEROAM_E_ARG, "heroam_gpu_run_sweep: null argument");
+  if (n_points < 1 || n_points > MAX_SWEEP_POINTS)
+    return fail(HEROAM_E_ARG, "heroam_gpu_run_sweep: %d points (1..%d supported per call)", n_points, MAX_SWEEP_POINTS);
   CU(cudaSetDevice(ctx->device));
-  memset(out, 0, sizeof *out);
+  memset(out, 0, (size_t)n_points * sizeof *out);
   memset(&ctx->info, 0, sizeof ctx->info);
   ctx->uploaded = false;
-  if (count == 0) return HEROAM_OK;
   Consts c;
   int rc = make_consts(ctx->conf, he_number, &c);
   if (rc) return rc;
-  const double lambda = host_lambda(ctx->conf, he_number);
-  if (!(lambda > 0.0) || lambda > 700.0)
-    return fail(HEROAM_E_ARG, "mean excitation number %g outside (0, 700]: Knuth's product of uniforms "
-                "(simulation.c:257-275) is undefined there", lambda);
-  const uint32_t cap = pool_slot_capacity(lambda);
+  PoolParams pool;
+  memset(&pool, 0, sizeof pool);
+  double lambda_max = 0.0;
+  unsigned long long count = 0;
+  for (int p = 0; p < n_points; ++p) {
+    const double lambda = point_lambda(ctx->conf, he_number, points[p].intensity, points[p].pulse_width);
+    if (!(lambda > 0.0) || lambda > 700.0)
+      return fail(HEROAM_E_ARG, "mean excitation number %g outside (0, 700]: Knuth's product of uniforms "
+                  "(simulation.c:257-275) is undefined there", lambda);
+    if (lambda > lambda_max) lambda_max = lambda;
+    count += points[p].count;
+    pool.point_end[p] = count;
+    pool.point_first[p] = points[p].first_index;
+    pool.point_limit[p] = exp(-1.0 * lambda);
+  }
+  if (count == 0) return HEROAM_OK;
+  const uint32_t cap = pool_slot_capacity(lambda_max);
   const unsigned long long pool_max = ctx->opt.pool_slots > 0 ? (unsigned long long)ctx->opt.pool_slots : (1ull << 22);
   const uint32_t slots = (uint32_t)(count < pool_max ? count : pool_max);
   rc = reserve(ctx, slots, (size_t)slots * cap);
@@ -552,32 +588,32 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
   ctx->n_particles = (size_t)slots * cap;
   DevBuf<DevStats> stats_buf;
   DevBuf<unsigned long long> cursor_buf;
-  CU(stats_buf.alloc(1));
+  CU(stats_buf.alloc((size_t)n_points));
   CU(cursor_buf.alloc(1));
   DevStats *d_stats = stats_buf.ptr;
   unsigned long long *d_cursor = cursor_buf.ptr;
-  PoolParams pool;
   pool.sp.seed = (long long)ctx->conf.seed;
   pool.sp.he_number = he_number;
-  pool.sp.first_index = first_index;
-  pool.sp.limit = exp(-1.0 * lambda);
+  pool.sp.first_index = 0;
+  pool.sp.limit = pool.point_limit[0];
   pool.sp.radius_init = 2.22 * pow((double)he_number, 1.0 / 3.0);
   pool.sp.sigma = ctx->conf.velocity;
   pool.cursor = d_cursor;
   pool.count = count;
   pool.cap = cap;
+  pool.n_points = (uint32_t)n_points;
   pool.stats = d_stats;
   CU(cudaEventRecord(ctx->ev_start, ctx->main));
-  CU(cudaMemsetAsync(d_stats, 0, sizeof(DevStats), ctx->main));
+  CU(cudaMemsetAsync(d_stats, 0, (size_t)n_points * sizeof(DevStats), ctx->main));
   CU(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->main));
   CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
   rc = ctx->opt.mode == HEROAM_MODE_EXACT        ? run_pool<Exact, Exact>(ctx, c, pool, slots)
        : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN ? run_pool<Fast, Fast>(ctx, c, pool, slots)
        : ctx->opt.count_work                     ? run_pool<Fast, TurboCount>(ctx, c, pool, slots)
                                                  : run_pool<Fast, Turbo>(ctx, c, pool, slots);
-  DevStats *h = (DevStats *)malloc(sizeof(DevStats));
+  std::vector<DevStats> h((size_t)n_points);
   if (rc == HEROAM_OK) {
-    if (cudaMemcpyAsync(h, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
+    if (cudaMemcpyAsync(h.data(), d_stats, (size_t)n_points * sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
         cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
         cudaEventRecord(ctx->ev_stop, ctx->main) != cudaSuccess || cudaStreamSynchronize(ctx->main) != cudaSuccess)
       rc = fail(HEROAM_E_CUDA, "statistics readback failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -586,27 +622,41 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
     ctx->info.device_ms = ms;
-    ctx->info.d2h_bytes = sizeof(DevStats);
-    ctx->info.trajectories = h->trajectories;
-    ctx->info.particles = h->particles;
+    ctx->info.d2h_bytes = (size_t)n_points * sizeof(DevStats);
     ctx->info.particle_steps = ctx->h_counters->particle_steps;
     ctx->info.pair_steps = ctx->h_counters->pair_steps;
     ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
     ctx->info.pair_skipped = ctx->h_counters->pair_skipped;
-  ctx->info.free_steps = ctx->h_counters->free_steps;
-    memcpy(out->hist_n, h->hist_n, sizeof out->hist_n);
-    memcpy(out->hist_traj_time, h->hist_traj_time, sizeof out->hist_traj_time);
-    memcpy(out->hist_meet_time, h->hist_meet_time, sizeof out->hist_meet_time);
-    memcpy(out->done, h->done, sizeof out->done);
-    out->unmet_particles = h->unmet_particles;
-    out->particles = h->particles;
-    out->trajectories = h->trajectories;
-    out->sum_traj_time = h->sum_traj_time;
-    out->info = ctx->info;
+    ctx->info.free_steps = ctx->h_counters->free_steps;
+    for (int p = 0; p < n_points; ++p) {
+      ctx->info.trajectories += h[p].trajectories;
+      ctx->info.particles += h[p].particles;
+    }
+    for (int p = 0; p < n_points; ++p) {
+      memcpy(out[p].hist_n, h[p].hist_n, sizeof out[p].hist_n);
+      memcpy(out[p].hist_traj_time, h[p].hist_traj_time, sizeof out[p].hist_traj_time);
+      memcpy(out[p].hist_meet_time, h[p].hist_meet_time, sizeof out[p].hist_meet_time);
+      memcpy(out[p].done, h[p].done, sizeof out[p].done);
+      out[p].unmet_particles = h[p].unmet_particles;
+      out[p].particles = h[p].particles;
+      out[p].trajectories = h[p].trajectories;
+      out[p].sum_traj_time = h[p].sum_traj_time;
+      out[p].info = ctx->info;  // work and timing of the whole sweep
+    }
     if (ctx->h_counters->unsupported)
       rc = fail(HEROAM_E_UNSUPPORTED, "%llu trajectories have more than %d particles", ctx->h_counters->unsupported,
                 MAX_ACTIVE);
   }
-  free(h);
   return rc;
+}
+
+extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index,
+                                    unsigned long long count, heroam_stats *out) {
+  if (!ctx || !out) return fail(HEROAM_E_ARG, "heroam_gpu_run_stats: null argument");
+  heroam_sweep_point point;
+  point.intensity = ctx->conf.intensity;
+  point.pulse_width = ctx->conf.pulse_width;
+  point.first_index = first_index;
+  point.count = count;
+  return heroam_gpu_run_sweep(ctx, he_number, 1, &point, out);
 }

@@ -46,6 +46,7 @@ ABI_SYMBOLS = (
     "heroam_gpu_sample_flat",
     "heroam_gpu_free_particles",
     "heroam_gpu_run_stats",
+    "heroam_gpu_run_sweep",
     "heroam_gpu_last_run_info",
     "heroam_gpu_fp32_peak",
     "heroam_gpu_fp32_peak_rrr",
@@ -108,6 +109,11 @@ class Stats(C.Structure):
 #: heroam_step_sink of include/heroam_gpu.h
 STEP_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32)
 
+class SweepPoint(C.Structure):
+    _fields_ = [("intensity", C.c_float), ("pulse_width", C.c_float), ("first_index", C.c_ulonglong),
+                ("count", C.c_ulonglong)]
+
+
 _lib = None
 
 
@@ -152,6 +158,8 @@ def load_library() -> C.CDLL:
     L.heroam_gpu_free_particles.argtypes = [C.POINTER(ParticlesC)]
     L.heroam_gpu_run_stats.restype = C.c_int
     L.heroam_gpu_run_stats.argtypes = [vp, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.POINTER(Stats)]
+    L.heroam_gpu_run_sweep.restype = C.c_int
+    L.heroam_gpu_run_sweep.argtypes = [vp, C.c_ulonglong, C.c_int, C.POINTER(SweepPoint), C.POINTER(Stats)]
     L.heroam_gpu_last_run_info.restype = C.c_int
     L.heroam_gpu_last_run_info.argtypes = [vp, C.POINTER(RunInfo)]
     L.heroam_gpu_fp32_peak.restype = C.c_int
@@ -305,9 +313,23 @@ class Engine:
             cap = total.value
 
     # -- fused statistics -------------------------------------------------------------
+    def run_sweep(self, he_number: int, points) -> list:
+        """``heroam_gpu_run_sweep``: points = [(intensity, pulse_width, count, first_index), ...];
+        one statistics dict per point."""
+        arr = (SweepPoint * len(points))()
+        for a, (intensity, pulse_width, count, first_index) in zip(arr, points):
+            a.intensity, a.pulse_width, a.count, a.first_index = intensity, pulse_width, count, first_index
+        out = (Stats * len(points))()
+        self._check(self.lib.heroam_gpu_run_sweep(self.handle, he_number, len(points), arr, out))
+        return [self._stats_dict(st) for st in out]
+
     def run_stats(self, he_number: int, count: int, first_index: int = 0) -> dict:
         st = Stats()
         self._check(self.lib.heroam_gpu_run_stats(self.handle, he_number, first_index, count, C.byref(st)))
+        return self._stats_dict(st)
+
+    @staticmethod
+    def _stats_dict(st) -> dict:
         return dict(
             trajectories=st.trajectories,
             particles=st.particles,

@@ -27,6 +27,16 @@ def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     return first, last - first
 
 
+def shard_sweep(points, rank: int, world: int):
+    """A rank's share of a laser sweep: every point (intensity, pulse_width, count, first_index)
+    keeps its place, its trajectories are split by index like a single run's."""
+    out = []
+    for intensity, pulse_width, count, first_index in points:
+        first, n = shard_range(count, rank, world)
+        out.append((intensity, pulse_width, n, first_index + first))
+    return out
+
+
 def stats_from_records(counts: np.ndarray, flat: np.ndarray, results: np.ndarray, max_time: float) -> dict:
     """Host-side equivalent of the device histogram kernel (k_stats), for batches whose
     final records were brought back to the host (the drop-in simulate path)."""

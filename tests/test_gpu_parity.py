@@ -113,6 +113,26 @@ def test_sparse_large_droplet_partner_lists(need_gpu, port, table):
     assert info["pair_skipped"] > 0.9 * info["pair_steps"], "the partner lists should skip almost every pair here"
 
 
+def test_large_table_gathers_from_hbm(need_gpu, port):
+    """The stress table of SURVEY.md 8d ("T-large"): same r^2 range on a 6e-5 A^2 grid, 26.6 M
+    entries = 106 MB in memory, so the gathers go past L1 to L2/HBM.  Same bits as the oracle."""
+    from sphere_roaming_b200.forcetable import synthetic_table
+
+    length, grid = 26_600_000, 6.0e-5
+    big = synthetic_table(length=length, grid=grid)
+    n, max_time = 512, 2.0e4
+    conf = make_config(number=n, max_time=max_time, force_grid=grid, force_grid_length=length, velocity=280.0)
+    counts, init = port.sample(conf, HE, big, n, source="philox")
+    want, wres, wctr = port.simulate(conf, HE, big, counts, init, want_counters=True)
+    with engine.Engine(conf, big, mode="exact") as eng:
+        got, res = eng.simulate(HE, counts, init)
+        info = eng.run_info()
+    assert_records_equal(got, want, "T-large")
+    assert np.array_equal(res["steps"], wres["steps"]) and np.array_equal(res["status"], wres["status"])
+    assert info["inrange_steps"] == wctr["inrange_steps"] > 0
+    assert (res["status"] == engine.DONE_SUCCESS).sum() > 32, "the batch should contain meetings"
+
+
 def test_fast_mode_within_stated_tolerance(need_gpu, port, table):
     n, max_time = 4096, 2.0e5
     conf = make_config(number=n, max_time=max_time)
