@@ -158,7 +158,7 @@ def cpu_run(table, max_time: float, n_traj: int, seed_offset: int = 0):
 
 def reference_arm(args, table):
     cores = os.cpu_count() or 1
-    sample = max(2 * cores, 32) if args.ref_sample <= 0 else args.ref_sample
+    sample = max(8 * cores, 32) if args.ref_sample <= 0 else args.ref_sample
     for w in range(args.warmup):
         cpu_run(table, args.max_time, min(sample, cores), seed_offset=1000 + w)
     tot_ps, tot_s, tot_traj = 0.0, 0.0, 0
@@ -240,6 +240,7 @@ def gpu_arm(args, table):
     eng = engine.Engine(conf, table, device=local, mode=args.mode, segment_steps=args.segment)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peak_tflops, clock_mhz = eng.fp32_peak()
+    peak_rrr_tflops = eng.fp32_peak_rrr()
 
     K, W = args.steps, args.warmup
 
@@ -351,6 +352,8 @@ def gpu_arm(args, table):
             "gpu_launches": tot_launches,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops * world, "unit": "TFLOP/s",
                          "frac": achieved / (peak_tflops * world), "traffic": traffic,
+                         "peak_three_register_ffma": peak_rrr_tflops * world,
+                         "frac_of_three_register_peak": achieved / (peak_rrr_tflops * world),
                          "frac_of_reference_work": tot_flops_ref / integ_s / 1e12 / (peak_tflops * world),
                          "free_flight_share_of_particle_steps": tot_free / tot_ps,
                          "inrange_share_of_evaluated_pairs": inrange_ratio,
@@ -358,14 +361,16 @@ def gpu_arm(args, table):
                                   "evaluated pair-step, +14 per in-range pair-step, over the CUDA-event time of the integrate "
                                   "kernels (frac_of_reference_work charges the SURVEY.md 8d model 100/10/14 for every step and "
                                   "pair the reference would evaluate); peak = register-resident FFMA "
-                                  "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                                  "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure), "
+                                  "multiplier in a uniform register; peak_three_register_ffma = the same chains with "
+                                  "multiplier and addend in ordinary registers, the form the kernels' FFMAs have",
                          "integrate_share_of_step": integ_s / dev_s},
             "exact_mode": exact,
             "outcomes": None if merged is None else {"success": int(merged["done"][0]), "max_time": int(merged["done"][1]),
                                                      "deadlock": int(merged["done"][2]), "trajectories": int(merged["trajectories"])},
         }
         if world == 1 and not args.no_cpu:
-            ps, s, n, cores, kind, flavour = cpu_run(table, args.max_time, max(2 * (os.cpu_count() or 1), 32))
+            ps, s, n, cores, kind, flavour = cpu_run(table, args.max_time, max(16 * (os.cpu_count() or 1), 64))
             line["cpu_baseline"] = {"value": ps / s, "unit": UNIT, "cores": cores, "kind": kind,
                                     "trajectories_per_sec": n / s,
                                     "sample": f"{n} trajectories of the same workload (libc-rand initial states), "
