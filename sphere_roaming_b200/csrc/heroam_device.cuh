@@ -116,6 +116,7 @@ struct DevView {       // everything a kernel needs, passed by value
 // arithmetic policies
 // ---------------------------------------------------------------------------------
 struct Exact {
+  static constexpr unsigned renorm_every = 1;  // steps between renormalisations of the orientation
   static constexpr bool exact = true;
   static constexpr bool turbo = false;
   static constexpr bool count = true;
@@ -146,6 +147,7 @@ struct Exact {
 };
 
 struct Fast {
+  static constexpr unsigned renorm_every = 1;
   static constexpr bool exact = false;
   static constexpr bool turbo = false;
   static constexpr bool count = true;
@@ -175,6 +177,10 @@ struct Turbo : Fast {
 struct TurboCount : Fast {
   static constexpr bool turbo = true;
   static constexpr bool count = true;
+};
+// Turbo that renormalises the orientation after every 8th step only (HEROAM_MODE_FAST_RELAXED)
+struct Turbo8 : Turbo {
+  static constexpr unsigned renorm_every = 8;
 };
 
 __device__ __forceinline__ float rsqrt_raw(float x) {  // one MUFU.RSQ, operands are never denormal here
@@ -239,8 +245,26 @@ __device__ __forceinline__ void half_kick(const Consts &c, const float r[3], con
 //   pole_position       : r = R * q (0,0,1) q^-1   (vector.c:94-110, :191-205, :182-188)
 // The position depends on nothing but the new q, so a particle that is guaranteed to feel
 // no force (free flight) only needs the first half per step and the second once at the end.
+// A policy with renorm_every = 8 (Turbo8) renormalises the orientation only after every 8th
+// step of a trajectory (absolute step index k with (k + 1) % 8 == 0).  q -> q + (dt/2) (0,w) q
+// is linear in q, so the direction of q -- all the position depends on -- is the same whether
+// the scale is taken out every step or every eighth; in between |q| wanders by float rounding
+// only (~1e-7: the exact growth per step is 1 + |w dt/2|^2 / 2 ~ 1 + 1e-11), which moves the
+// closed-form pole image by ~1e-5 A.  Keyed to the ABSOLUTE step, the result does not depend
+// on how a trajectory's steps are cut into segments and kernels.  What it does change is the
+// rounding pattern: the per-step roundings no longer mirror the reference's one for one, so the
+// two orientations random-walk apart at the rate at which each random-walks away from the
+// exact solution (measured: ~1.6e-3 A median after 2e5 steps instead of 2e-5 A).
+constexpr uint32_t RENORM_ALIGN = 8;  // segment ends are multiples of this (the largest renorm_every)
+
+// true if the step with absolute index `step` ends with a renormalisation
 template <class P>
-__device__ __forceinline__ void advance_orientation(const Consts &c, const float w[3], float q[4]) {
+__device__ __forceinline__ bool renorm_at(uint32_t step) {
+  return P::renorm_every == 1u || ((step + 1u) & (P::renorm_every - 1u)) == 0u;
+}
+
+template <class P>
+__device__ __forceinline__ void advance_orientation(const Consts &c, const float w[3], float q[4], const bool renorm) {
   const float qa = q[0], qx = q[1], qy = q[2], qz = q[3];
   const float ox = w[0], oy = w[1], oz = w[2];
   if (P::exact) {
@@ -265,10 +289,13 @@ __device__ __forceinline__ void advance_orientation(const Consts &c, const float
     const float nx = qx + fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
     const float ny = qy + fmaf(oz, qx, fmaf(-ox, qz, oy * qa));
     const float nz = qz + fmaf(oz, qa, fmaf(-oy, qx, ox * qy));
-    const float inv = rsqrt_raw(fmaf(nz, nz, fmaf(ny, ny, fmaf(nx, nx, na * na))));
-    // __fmul_rn: a plain product could be contracted by the compiler into whatever addition
-    // consumes it next (differently in different kernels); the state must not depend on that
-    q[0] = __fmul_rn(na, inv); q[1] = __fmul_rn(nx, inv); q[2] = __fmul_rn(ny, inv); q[3] = __fmul_rn(nz, inv);
+    q[0] = na; q[1] = nx; q[2] = ny; q[3] = nz;
+    if (renorm) {  // a real branch: uniform across the warp whenever its trajectories are in phase
+      const float inv = rsqrt_raw(fmaf(nz, nz, fmaf(ny, ny, fmaf(nx, nx, na * na))));
+      // __fmul_rn: a plain product could be contracted by the compiler into whatever addition
+      // consumes it next (differently in different kernels); the state must not depend on that
+      q[0] = __fmul_rn(na, inv); q[1] = __fmul_rn(nx, inv); q[2] = __fmul_rn(ny, inv); q[3] = __fmul_rn(nz, inv);
+    }
   } else {
     const float ta = -fmaf(oz, qz, fmaf(oy, qy, ox * qx));
     const float tx = fmaf(-oz, qy, fmaf(oy, qz, ox * qa));
@@ -281,6 +308,13 @@ __device__ __forceinline__ void advance_orientation(const Consts &c, const float
     const float inv = rsqrtf(P::dot4(na, nx, ny, nz));
     q[0] = __fmul_rn(na, inv); q[1] = __fmul_rn(nx, inv); q[2] = __fmul_rn(ny, inv); q[3] = __fmul_rn(nz, inv);
   }
+}
+
+// the renormalisation on its own (Turbo): lets a kernel that holds several particles take ONE
+// branch per step around all of them
+__device__ __forceinline__ void renormalise(float q[4]) {
+  const float inv = rsqrt_raw(fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0]))));
+  q[0] = __fmul_rn(q[0], inv); q[1] = __fmul_rn(q[1], inv); q[2] = __fmul_rn(q[2], inv); q[3] = __fmul_rn(q[3], inv);
 }
 
 template <class P>
@@ -313,8 +347,8 @@ __device__ __forceinline__ void pole_position(const Consts &c, const float q[4],
 }
 
 template <class P>
-__device__ __forceinline__ void drift(const Consts &c, const float w[3], float q[4], float r[3]) {
-  advance_orientation<P>(c, w, q);
+__device__ __forceinline__ void drift(const Consts &c, const float w[3], float q[4], float r[3], const bool renorm) {
+  advance_orientation<P>(c, w, q, renorm);
   pole_position<P>(c, q, r);
 }
 

@@ -173,7 +173,8 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   ctx->conf = *conf;
   memset(&ctx->opt, 0, sizeof ctx->opt);
   if (opt) ctx->opt = *opt;
-  if (ctx->opt.mode != HEROAM_MODE_EXACT && ctx->opt.mode != HEROAM_MODE_FAST && ctx->opt.mode != HEROAM_MODE_FAST_PLAIN) {
+  if (ctx->opt.mode != HEROAM_MODE_EXACT && ctx->opt.mode != HEROAM_MODE_FAST && ctx->opt.mode != HEROAM_MODE_FAST_PLAIN &&
+      ctx->opt.mode != HEROAM_MODE_FAST_RELAXED) {
     delete ctx;
     return fail(HEROAM_E_ARG, "unknown mode %d", opt->mode);
   }
@@ -251,7 +252,8 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
 
 extern "C" int heroam_gpu_set_mode(heroam_ctx *ctx, int mode) {
   if (!ctx) return fail(HEROAM_E_ARG, "null context");
-  if (mode != HEROAM_MODE_EXACT && mode != HEROAM_MODE_FAST && mode != HEROAM_MODE_FAST_PLAIN)
+  if (mode != HEROAM_MODE_EXACT && mode != HEROAM_MODE_FAST && mode != HEROAM_MODE_FAST_PLAIN &&
+      mode != HEROAM_MODE_FAST_RELAXED)
     return fail(HEROAM_E_ARG, "unknown mode %d", mode);
   ctx->opt.mode = mode;
   return HEROAM_OK;
@@ -462,7 +464,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     Segments sg = make_segments(ctx->opt.segment_steps, draining, split_window_max(ctx));
     sg.free_stride = ctx->free_stride;
-    k_resolve_and_bin<R><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
+    k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
@@ -531,8 +533,9 @@ extern "C" int heroam_gpu_run(heroam_ctx *ctx) {
   if (rc) return rc;
   ctx->uploaded = false;  // the resident batch is consumed
   if (ctx->n_traj == 0) return HEROAM_OK;
-  rc = ctx->opt.mode == HEROAM_MODE_EXACT        ? run_passes<Exact, Exact>(ctx, c)
-       : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN ? run_passes<Fast, Fast>(ctx, c)
+  rc = ctx->opt.mode == HEROAM_MODE_EXACT          ? run_passes<Exact, Exact>(ctx, c)
+       : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN   ? run_passes<Fast, Fast>(ctx, c)
+       : ctx->opt.mode == HEROAM_MODE_FAST_RELAXED ? run_passes<Fast, Turbo8>(ctx, c)
        : ctx->opt.count_work                     ? run_passes<Fast, TurboCount>(ctx, c)
                                                  : run_passes<Fast, Turbo>(ctx, c);
   return rc;
@@ -670,7 +673,7 @@ static int run_traced(heroam_ctx *ctx, const Consts &c, const uint32_t *counts, 
   int rc = HEROAM_OK;
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
-    k_resolve_and_bin<R><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
+    k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));

@@ -503,7 +503,7 @@ __device__ inline void rewind_loners(const DevView &v, TrajMeta &m, Counters &wo
     load_w<P>(c, w_rec, w);
     float time = m.loner_time0;
     for (uint32_t k = m.loner_from; k < m.steps; ++k) {
-      advance_orientation<P>(c, w, q);
+      advance_orientation<P>(c, w, q, renorm_at<P>(k));
       time = __fadd_rn(time, c.dt);
     }
     pole_position<P>(c, q, r);
@@ -558,6 +558,7 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
     for (uint32_t i = 0; i < m.n_loners; ++i) act[s + i] = lon[i];
     if (m.n_active > 0) {
       uint32_t stop = m.steps + sg.of_bin[BIN_CORE + (int)m.n_active];
+      if (stop >= m.steps && stop - m.steps >= 2u * RENORM_ALIGN) stop &= ~(RENORM_ALIGN - 1u);
       if (stop < m.steps || stop > m.loner_until) stop = m.loner_until;
       m.step_stop = stop;
       out.bin = BIN_CORE + (int)m.n_active;
@@ -583,6 +584,8 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
   const bool one_step_only = m.steps == 0 && all_paired(m.no, m.n_flagged);  // Q2
   auto clip = [&](uint32_t stop) {
     if (stop < m.steps) stop = 0xffffffffu;
+    // segments end on renormalisation boundaries, so that the trajectories of a warp stay in phase
+    if (stop - m.steps >= 2u * RENORM_ALIGN) stop &= ~(RENORM_ALIGN - 1u);
     if (one_step_only) stop = 1;
     if (stop > v.c.max_steps) stop = v.c.max_steps;
     if (stop > step_cap) stop = step_cap;
@@ -692,13 +695,15 @@ __device__ inline void flush_work(const DevView &v, const Counters &work) {
 }
 
 // One resolve visit of a live trajectory: returns what to launch for it (nothing if it ended).
-template <class P>
+// P: arithmetic of the meeting step; H: arithmetic of the integrate kernels (a rewound loner
+// must be re-flown exactly as k_free_flight<H> flew it).
+template <class P, class H>
 __device__ inline Schedule resolve_live(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap,
                                         Counters &work) {
   settle<P>(v, m, work);
   const uint32_t done = evaluate_exit(v.c, m, step_cap);
   if (done != NOT_DONE) {
-    if (m.n_loners && m.loner_until > m.steps) rewind_loners<P>(v, m, work);
+    if (m.n_loners && m.loner_until > m.steps) rewind_loners<H>(v, m, work);
     m.status = ST_DONE + done;
     if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported += 1;
     return Schedule();
@@ -709,7 +714,7 @@ __device__ inline Schedule resolve_live(const DevView &v, TrajMeta &m, const Seg
 // ---------------------------------------------------------------------------------
 // k_resolve_and_bin: one thread per trajectory, once per pass (fixed batch).
 // ---------------------------------------------------------------------------------
-template <class P>
+template <class P, class H>
 __global__ void k_resolve_and_bin(DevView v, Segments sg, uint32_t step_cap, uint32_t *__restrict__ bin_count,
                                   uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -718,7 +723,7 @@ __global__ void k_resolve_and_bin(DevView v, Segments sg, uint32_t step_cap, uin
   if (t < v.n_traj) {
     TrajMeta m = v.meta[t];
     if (m.status < ST_DONE) {
-      sc = resolve_live<P>(v, m, sg, step_cap, work);
+      sc = resolve_live<P, H>(v, m, sg, step_cap, work);
       v.meta[t] = m;
     }
   }
@@ -752,8 +757,24 @@ __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__r
   float w[3], w_rec[3];
   ld3(p->ang_velocity, w_rec);
   load_w<P>(c, w_rec, w);
-  for (uint32_t k = from; k < until; ++k) {
-    advance_orientation<P>(c, w, q);
+  uint32_t k = from;
+  if (P::renorm_every > 1u) {
+    // renormalisation after every renorm_every-th absolute step: single steps up to the next
+    // boundary, then whole blocks without any test, then the remainder
+    for (; k < until && (k & (P::renorm_every - 1u)) != 0u; ++k) {
+      advance_orientation<P>(c, w, q, renorm_at<P>(k));
+      time = __fadd_rn(time, c.dt);
+    }
+    for (; k + P::renorm_every <= until; k += P::renorm_every) {
+#pragma unroll
+      for (uint32_t u = 0; u < P::renorm_every; ++u) {
+        advance_orientation<P>(c, w, q, u + 1u == P::renorm_every);
+        time = __fadd_rn(time, c.dt);
+      }
+    }
+  }
+  for (; k < until; ++k) {
+    advance_orientation<P>(c, w, q, renorm_at<P>(k));
     time = __fadd_rn(time, c.dt);
   }
   float r[3], vel[3], v2;
@@ -808,6 +829,7 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
 #pragma unroll
     for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) { pos_prev[i] = 0.0f; tv_ahead[i] = 0.0f; bin_ahead[i] = 0xffffffffu; }
     while (steps < m.step_stop) {
+      const bool rn = renorm_at<P>(steps);
       // first half kick + drift (simulation.c:478-490)
 #pragma unroll
       for (int s = 0; s < A; ++s) {
@@ -815,7 +837,15 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
         wh[s][0] = P::add(w[s][0], hk[s][0]);
         wh[s][1] = P::add(w[s][1], hk[s][1]);
         wh[s][2] = P::add(w[s][2], hk[s][2]);
-        drift<P>(c, wh[s], q[s], r[s]);
+        advance_orientation<P>(c, wh[s], q[s], P::renorm_every == 1u);
+      }
+      if (P::renorm_every > 1u && rn) {  // one branch per step for all particles; uniform when the warp is in phase
+#pragma unroll
+        for (int s = 0; s < A; ++s) renormalise(q[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < A; ++s) {
+        pole_position<P>(c, q[s], r[s]);
         f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
       }
       // all pairs in the reference's (j,k) order (:178-233)
@@ -928,6 +958,7 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_hybrid(DevView v, const 
     float time = m.time;
     bool met = false;
     while (steps < m.step_stop) {
+      const bool rn = renorm_at<P>(steps);
 #pragma unroll
       for (int s = 0; s < A; ++s) {
         const float4 w4 = ws[s * SMEM_TPB], q4 = qs[s * SMEM_TPB];
@@ -937,7 +968,7 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_hybrid(DevView v, const 
         ws[s * SMEM_TPB] = make_float4(w4.x, w4.y, w4.z, r[s][0]);
         hs[s * SMEM_TPB] = make_float4(wh[0], wh[1], wh[2], r[s][1]);
         zs[s * SMEM_TPB] = r[s][2];
-        drift<P>(c, wh, q, r[s]);
+        drift<P>(c, wh, q, r[s], rn);
         qs[s * SMEM_TPB] = make_float4(q[0], q[1], q[2], q[3]);
         f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
       }
@@ -1038,17 +1069,18 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_smem(DevView v, const ui
     float time = m.time;
     bool met = false;
     while (steps < m.step_stop) {
+      const bool rn = renorm_at<P>(steps);
       // first half kick + drift
 #pragma unroll 2
       for (uint32_t s = 0; s < a; ++s) {
         const float4 r4 = COL(pos, s), f4 = COL(frc, s), q4 = COL(qq, s), w4 = COL(ww, s);
         const float r[3] = {r4.x, r4.y, r4.z}, f[3] = {f4.x, f4.y, f4.z};
-        float hk[3], wh[3], q[4] = {q4.x, q4.y, q4.z, q4.w}, rn[3];
+        float hk[3], wh[3], q[4] = {q4.x, q4.y, q4.z, q4.w}, r_new[3];
         half_kick<P>(c, r, f, hk);
         wh[0] = P::add(w4.x, hk[0]); wh[1] = P::add(w4.y, hk[1]); wh[2] = P::add(w4.z, hk[2]);
-        drift<P>(c, wh, q, rn);
+        drift<P>(c, wh, q, r_new, rn);
         COL(qq, s) = make_float4(q[0], q[1], q[2], q[3]);
-        COL(pos, s) = make_float4(rn[0], rn[1], rn[2], r4.x);
+        COL(pos, s) = make_float4(r_new[0], r_new[1], r_new[2], r4.x);
         COL(frc, s) = make_float4(0.0f, 0.0f, 0.0f, r4.y);
         COL(ww, s) = make_float4(w4.x, w4.y, w4.z, r4.z);
         COL(whh, s) = make_float4(wh[0], wh[1], wh[2], 0.0f);
@@ -1204,6 +1236,7 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count, b
   bool met = false;
   unsigned long long inrange_total = 0;
   while (steps < m.step_stop) {
+    const bool rn = renorm_at<P>(steps);  // one trajectory per warp: uniform
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
       if (own[i]) {
@@ -1211,7 +1244,7 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count, b
         wh[i][0] = P::add(w[i][0], hk[i][0]);
         wh[i][1] = P::add(w[i][1], hk[i][1]);
         wh[i][2] = P::add(w[i][2], hk[i][2]);
-        drift<P>(c, wh[i], q[i], r[i]);
+        drift<P>(c, wh[i], q[i], r[i], rn);
         pos[lane + 32u * i] = make_float4(r[i][0], r[i][1], r[i][2], 0.0f);
       }
       f[i][0] = 0.0f; f[i][1] = 0.0f; f[i][2] = 0.0f;
@@ -1326,7 +1359,7 @@ __global__ void k_integrate_records(DevView v, const uint32_t *__restrict__ list
       wh[1] = P::add(p->ang_velocity[1], hk[1]);
       wh[2] = P::add(p->ang_velocity[2], hk[2]);
       q[0] = p->orientation[0]; q[1] = p->orientation[1]; q[2] = p->orientation[2]; q[3] = p->orientation[3];
-      drift<P>(c, wh, q, r);
+      drift<P>(c, wh, q, r, renorm_at<P>(m.steps));
       p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
       st3(p->position, r);
       st3(p->force, wh);  // scratch slot: w(t + dt/2)
@@ -1426,7 +1459,7 @@ __global__ void k_integrate_capture(DevView v, CaptureView cap, const uint32_t *
       wh[1] = P::add(p->ang_velocity[1], hk[1]);
       wh[2] = P::add(p->ang_velocity[2], hk[2]);
       q[0] = p->orientation[0]; q[1] = p->orientation[1]; q[2] = p->orientation[2]; q[3] = p->orientation[3];
-      drift<P>(c, wh, q, r);
+      drift<P>(c, wh, q, r, renorm_at<P>(m.steps));
       p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
       st3(p->position, r);
       st3(p->force, wh);  // scratch slot: w(t + dt/2)

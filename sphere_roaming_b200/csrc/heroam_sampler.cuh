@@ -310,7 +310,7 @@ __global__ void k_pool_init(DevView v, uint32_t cap) {
   v.meta[t] = m;
 }
 
-template <class P>
+template <class P, class H>
 __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t step_cap,
                                uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list,
                                uint2 *__restrict__ free_list) {
@@ -322,7 +322,7 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
     // a freshly spawned trajectory can be over at once (nobody moving), hence the loop
     for (;;) {
       if (m.status < ST_DONE) {
-        sc = resolve_live<P>(v, m, sg, step_cap, work);
+        sc = resolve_live<P, H>(v, m, sg, step_cap, work);
         if (m.status < ST_DONE) break;  // still live: scheduled
       }
       if (m.status != ST_FREE) {
@@ -493,7 +493,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     Segments sg = make_segments(ctx->opt.segment_steps, draining, split_window_max(ctx));
     sg.free_stride = ctx->free_stride;
-    k_pool_resolve<R><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
+    k_pool_resolve<R, H><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
                                                      ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
@@ -607,8 +607,9 @@ extern "C" int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_numbe
   CU(cudaMemsetAsync(d_stats, 0, (size_t)n_points * sizeof(DevStats), ctx->main));
   CU(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->main));
   CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
-  rc = ctx->opt.mode == HEROAM_MODE_EXACT        ? run_pool<Exact, Exact>(ctx, c, pool, slots)
-       : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN ? run_pool<Fast, Fast>(ctx, c, pool, slots)
+  rc = ctx->opt.mode == HEROAM_MODE_EXACT          ? run_pool<Exact, Exact>(ctx, c, pool, slots)
+       : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN   ? run_pool<Fast, Fast>(ctx, c, pool, slots)
+       : ctx->opt.mode == HEROAM_MODE_FAST_RELAXED ? run_pool<Fast, Turbo8>(ctx, c, pool, slots)
        : ctx->opt.count_work                     ? run_pool<Fast, TurboCount>(ctx, c, pool, slots)
                                                  : run_pool<Fast, Turbo>(ctx, c, pool, slots);
   std::vector<DevStats> h((size_t)n_points);

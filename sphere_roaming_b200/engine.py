@@ -19,7 +19,9 @@ LIB_PATH = os.path.join(_HERE, "libheroam_gpu.so")
 MODE_EXACT = 0
 MODE_FAST = 1
 MODE_FAST_PLAIN = 2
-_MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, "fast_plain": MODE_FAST_PLAIN, 0: MODE_EXACT, 1: MODE_FAST, 2: MODE_FAST_PLAIN}
+MODE_FAST_RELAXED = 3
+_MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, "fast_plain": MODE_FAST_PLAIN, "fast_relaxed": MODE_FAST_RELAXED,
+          0: MODE_EXACT, 1: MODE_FAST, 2: MODE_FAST_PLAIN, 3: MODE_FAST_RELAXED}
 
 DONE_SUCCESS, DONE_MAXTIME, DONE_DEADLOCK, DONE_STEPCAP, DONE_UNSUPPORTED = 0, 1, 2, 4, 6
 

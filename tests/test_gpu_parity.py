@@ -133,12 +133,20 @@ def test_large_table_gathers_from_hbm(need_gpu, port):
     assert (res["status"] == engine.DONE_SUCCESS).sum() > 32, "the batch should contain meetings"
 
 
-def test_fast_mode_within_stated_tolerance(need_gpu, port, table):
+#: stated position tolerance [A] after 2e5 steps, trajectories with identical exit step: (median, 99 %)
+POSITION_TOLERANCE = {
+    "fast": (2e-4, 5e-3),          # measured 2.4e-5 / 6.0e-4: the roundings mirror the reference's step for step
+    "fast_relaxed": (5e-3, 1e-1),  # measured 1.6e-3 / 2.3e-2: renormalisation every 8th step, independent rounding walk
+}
+
+
+@pytest.mark.parametrize("mode", ["fast", "fast_relaxed"])
+def test_fast_mode_within_stated_tolerance(need_gpu, port, table, mode):
     n, max_time = 4096, 2.0e5
     conf = make_config(number=n, max_time=max_time)
     counts, init = port.sample(conf, HE, table, n, source="philox")
     want, wres = port.simulate(conf, HE, table, counts, init)
-    with engine.Engine(conf, table, mode="fast") as eng:
+    with engine.Engine(conf, table, mode=mode) as eng:
         got, res = eng.simulate(HE, counts, init)
     off = offsets_of(counts)
     dt = np.abs(res["time"].astype(np.float64) - wres["time"])
@@ -150,7 +158,8 @@ def test_fast_mode_within_stated_tolerance(need_gpu, port, table):
     assert np.array_equal(res["status"] == 1, wres["status"] == 1) or ((res["status"] == 1) != (wres["status"] == 1)).mean() < 0.01
     same_step = np.repeat(res["steps"] == wres["steps"], counts)
     dr = np.abs(got["position"].astype(np.float64) - want["position"]).max(axis=1)[same_step & (got["time"] == want["time"])]
-    assert np.median(dr) < 2e-4 and np.quantile(dr, 0.99) < 5e-3, (np.median(dr), dr.max())
+    tol_median, tol_99 = POSITION_TOLERANCE[mode]
+    assert np.median(dr) < tol_median and np.quantile(dr, 0.99) < tol_99, (np.median(dr), np.quantile(dr, 0.99), dr.max())
     # radius is preserved by the re-projection
     R = port.radius_sim(HE)
     assert np.allclose(np.linalg.norm(got["position"].astype(np.float64), axis=1), R, rtol=3e-6)
@@ -313,4 +322,14 @@ def test_full_size_properties(need_gpu, port, table):
     for key in ("hist_n", "hist_traj_time", "hist_meet_time", "done"):
         assert np.array_equal(whole[key], a[key] + b[key]), key
     assert whole["trajectories"] == n
+    # the relaxed mode keys its renormalisation to the absolute step, so it too is independent of
+    # how the index space is cut and of what else shares the pool
+    with engine.Engine(conf, table, mode="fast_relaxed") as eng:
+        whole_r = eng.run_stats(HE, n)
+        parts_r = [eng.run_stats(HE, n // 4, first_index=k * (n // 4)) for k in range(4)]
+        batch_r, _ = eng.simulate(HE, counts[:4096], init[:off[4096]])
+        batch_again, _ = eng.simulate(HE, counts[1000:4096], init[off[1000]:off[4096]])
+    for key in ("hist_n", "hist_traj_time", "hist_meet_time", "done"):
+        assert np.array_equal(whole_r[key], sum(p[key] for p in parts_r)), key
+    assert batch_r[off[1000]:].tobytes() == batch_again.tobytes(), "a trajectory's result must not depend on its batch"
     assert np.array_equal(whole["hist_n"][:64], np.bincount(counts, minlength=64)[:64])

@@ -16,14 +16,15 @@ HE = 10000
 P_MIN = 1e-3
 
 
-def test_histograms_agree_with_reference_distribution(port, table):
+@pytest.mark.parametrize("mode", ["fast", "fast_relaxed"])
+def test_histograms_agree_with_reference_distribution(port, table, mode):
     if engine.device_count() < 1:
         pytest.fail("needs a CUDA device")
     max_time, n_gpu, n_cpu = 1.0e5, 200_000, 3000
     conf = make_config(number=n_cpu, max_time=max_time)
     counts, init = port.sample(conf, HE, table, n_cpu, source="rand")     # the reference's sampler
     final, res = port.simulate(conf, HE, table, counts, init)              # the reference's integrator
-    with engine.Engine(make_config(number=n_gpu, max_time=max_time), table, mode="fast") as eng:
+    with engine.Engine(make_config(number=n_gpu, max_time=max_time), table, mode=mode) as eng:
         st = eng.run_stats(HE, n_gpu, first_index=10**6)
     assert st["trajectories"] == n_gpu
     # excitation count: exact zero-truncated Poisson pmf
