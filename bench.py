@@ -136,8 +136,10 @@ def cpu_run(table, max_time: float, n_traj: int, seed_offset: int = 0):
     workload).  Returns (particle_steps, seconds, trajectories, cores, kind)."""
     ref, kind, flavour = pick_ref_oracle()
     conf = make_config(number=n_traj, max_time=max_time, seed=100401452 + seed_offset)
+    # every host core, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+    all_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if ref is not None:
-        cores = ref.max_threads()
+        cores = max(ref.max_threads(), all_cores)
         counts, init = ref.initialize(conf, HE, table)
         t0 = time.perf_counter()
         final = ref.simulate(conf, HE, table, counts, init, nthreads=cores, dynamic=True)
@@ -146,7 +148,7 @@ def cpu_run(table, max_time: float, n_traj: int, seed_offset: int = 0):
         from oracle.binding import PortOracle
 
         port = PortOracle()
-        cores = port.max_threads()
+        cores = max(port.max_threads(), all_cores)
         counts, init = port.sample(conf, HE, table, n_traj, source="rand")
         t0 = time.perf_counter()
         final, _ = port.simulate(conf, HE, table, counts, init, nthreads=cores)

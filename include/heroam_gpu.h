@@ -236,6 +236,8 @@ int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_clock_mhz);
 /* The same with both the multiplier and the addend in registers (three register operands per
  * FFMA, as in the integrate kernels) instead of the constant bank. */
 int heroam_gpu_fp32_peak_rrr(heroam_ctx *ctx, double *tflops);
+/* The same chains as packed FFMA2 (two FP32 lanes per 64-bit register pair, three register operands). */
+int heroam_gpu_fp32_peak_x2(heroam_ctx *ctx, double *tflops);
 
 #ifdef __cplusplus
 }

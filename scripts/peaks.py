@@ -7,5 +7,7 @@ from sphere_roaming_b200.types import make_config
 with engine.Engine(make_config(), synthetic_table()) as eng:
     a, mhz = eng.fp32_peak()
     b = eng.fp32_peak_rrr()
+    x2 = eng.fp32_peak_x2()
     print("FFMA reg x uniform + reg : %.2f TFLOP/s  (clock attr %.0f MHz)" % (a, mhz))
     print("FFMA reg x reg + reg     : %.2f TFLOP/s  (%.3f of the former)" % (b, b / a))
+    print("FFMA2 packed, 3 registers : %.2f TFLOP/s  (%.3f of the first)" % (x2, x2 / a))

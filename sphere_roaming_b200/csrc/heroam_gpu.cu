@@ -822,6 +822,32 @@ extern "C" int heroam_gpu_fp32_peak(heroam_ctx *ctx, double *tflops, double *sm_
   return HEROAM_OK;
 }
 
+extern "C" int heroam_gpu_fp32_peak_x2(heroam_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return fail(HEROAM_E_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  DevBuf<float> out_buf, coef_buf;
+  CU(out_buf.alloc(1));
+  CU(coef_buf.alloc(8));
+  const float coef[8] = {0.999f, 0.998f, 0.997f, 0.996f, 0.001f, 0.002f, 0.003f, 0.004f};
+  CU(cudaMemcpy(coef_buf.ptr, coef, sizeof coef, cudaMemcpyHostToDevice));
+  const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(ctx->ev_c0, ctx->main));
+    k_fma_peak_x2<<<blocks, threads, 0, ctx->main>>>(out_buf.ptr, coef_buf.ptr, iters);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_c1, ctx->main));
+    CU(cudaStreamSynchronize(ctx->main));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev_c0, ctx->ev_c1));
+    const double flops = 2.0 * 16.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  *tflops = best;
+  return HEROAM_OK;
+}
+
 extern "C" int heroam_gpu_fp32_peak_rrr(heroam_ctx *ctx, double *tflops) {
   if (!ctx || !tflops) return fail(HEROAM_E_ARG, "null argument");
   CU(cudaSetDevice(ctx->device));

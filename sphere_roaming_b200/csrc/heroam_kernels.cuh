@@ -1569,4 +1569,22 @@ __global__ void __launch_bounds__(256) k_fma_peak_rrr(float *out, const float *_
   if (s == 12345.678f) out[0] = s;
 }
 
+// Packed FP32 (FFMA2 on 64-bit register pairs, sm_100): the same chains, two per instruction.
+__global__ void __launch_bounds__(256) k_fma_peak_x2(float *out, const float *__restrict__ coef, int iters) {
+  const float t = threadIdx.x;
+  float2 x0 = make_float2(t, t + 1), x1 = make_float2(t + 2, t + 3), x2 = make_float2(t + 4, t + 5), x3 = make_float2(t + 6, t + 7);
+  float2 x4 = make_float2(t + 8, t + 9), x5 = make_float2(t + 10, t + 11), x6 = make_float2(t + 12, t + 13), x7 = make_float2(t + 14, t + 15);
+  const float2 a0 = make_float2(coef[0], coef[1]), a1 = make_float2(coef[2], coef[3]);
+  const float2 b0 = make_float2(coef[4], coef[5]), b1 = make_float2(coef[6], coef[7]);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = __ffma2_rn(x0, a0, b0); x1 = __ffma2_rn(x1, a1, b1); x2 = __ffma2_rn(x2, a0, b1); x3 = __ffma2_rn(x3, a1, b0);
+      x4 = __ffma2_rn(x4, a0, b0); x5 = __ffma2_rn(x5, a1, b1); x6 = __ffma2_rn(x6, a0, b1); x7 = __ffma2_rn(x7, a1, b0);
+    }
+  }
+  const float s = ((x0.x + x1.x) + (x2.x + x3.x)) + ((x4.x + x5.x) + (x6.x + x7.x)) + ((x0.y + x1.y) + (x2.y + x3.y)) + ((x4.y + x5.y) + (x6.y + x7.y));
+  if (s == 12345.678f) out[0] = s;
+}
+
 }  // namespace heroam

@@ -52,6 +52,7 @@ ABI_SYMBOLS = (
     "heroam_gpu_last_run_info",
     "heroam_gpu_fp32_peak",
     "heroam_gpu_fp32_peak_rrr",
+    "heroam_gpu_fp32_peak_x2",
 )
 
 
@@ -168,6 +169,8 @@ def load_library() -> C.CDLL:
     L.heroam_gpu_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.heroam_gpu_fp32_peak_rrr.restype = C.c_int
     L.heroam_gpu_fp32_peak_rrr.argtypes = [vp, C.POINTER(C.c_double)]
+    L.heroam_gpu_fp32_peak_x2.restype = C.c_int
+    L.heroam_gpu_fp32_peak_x2.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -357,4 +360,9 @@ class Engine:
     def fp32_peak_rrr(self) -> float:
         tf = C.c_double(0)
         self._check(self.lib.heroam_gpu_fp32_peak_rrr(self.handle, C.byref(tf)))
+        return tf.value
+
+    def fp32_peak_x2(self) -> float:
+        tf = C.c_double(0)
+        self._check(self.lib.heroam_gpu_fp32_peak_x2(self.handle, C.byref(tf)))
         return tf.value
