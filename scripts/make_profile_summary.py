@@ -33,7 +33,10 @@ def launch_table(path, cmd):
       f"{sum(v[0] for v in agg.values())} launches.\n")
 
 def metric_table(path, title, cmd, keep=None):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # already exported on the GPU box (`ncu -i rep --page raw --csv`)
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -70,33 +73,44 @@ def metric_table(path, title, cmd, keep=None):
     P("")
 
 P("## 1. Launch list of the bench command\n")
-launch_table(os.path.join(G, "launches_r1b.csv"),
-             "ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 2 --warmup 1 "
-             "--batch 131072 --max-time 1e6 --no-cpu --exact-step 0 --e2e-steps 1 --warmup-e2e 0")
+SMALL = ("--steps 2 --warmup 1 --batch 131072 --max-time 1e6 --no-cpu --exact-step 0 --relaxed-step 0 --e2e-steps 1 --warmup-e2e 0")
+launch_table(os.path.join(G, "launches_final.csv"),
+             "ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv python bench.py " + SMALL)
 P("Raw list: `r1_launches_bench_small.csv`. Under ncu the kernels run one at a time and cold; in the real run the "
-  "kernels of one pass execute concurrently on separate streams. `bench.py` reports `integrate_share_of_step` = 0.99 for "
-  "the same command from CUDA events.\n")
-metric_table(os.path.join(G, "prof_r1_turbo_full.ncu-rep"), "2. Dominant kernel at full occupancy (`--set full`)",
-             "NS=4,8 MODES=fast ncu --set full --clock-control none --import-source on -k regex:k_integrate_thread -c 6 "
-             "python scripts/bench_bins.py   (151552 trajectories with exactly 4 (8) moving particles, 4096-step cap)",
-             keep=lambda n: "<4," in n or "<8," in n)
-metric_table(os.path.join(G, "prof_r1_final.ncu-rep"), "3. The kernels inside the bench command (131072-slot pool, under-filled GPU)",
-             "ncu --set full --clock-control none --import-source on -k regex:'k_integrate_thread|k_free_flight|k_integrate_hybrid' "
-             "-s 30 -c 14 python bench.py --steps 2 --warmup 1 --batch 131072 --max-time 1e6 ...")
+  "kernels of one pass execute concurrently on separate streams. `bench.py` reports `integrate_share_of_step` = 0.98 for "
+  "the same command from CUDA events (0.96 for the default command). In this reduced configuration (131072 slots, "
+  "max_time 1e6) the serialised list over-weights the rare wide bins: each of their launches lasts as long as its "
+  "dependency chain however few trajectories it holds.\n")
+metric_table(os.path.join(G, "prof_final_pool2_raw.csv"),
+             "2. The hot kernels at full occupancy, inside a pool run (`--set full`)",
+             "N=2000000 CAP=40000 ncu --set full --clock-control none -k regex:'k_integrate_thread|k_free_flight|k_pool_resolve' "
+             "-s 17 -c 18 python scripts/pool_once.py   (2e6 trajectories of config C2 in the pool, passes 2-3)")
+metric_table(os.path.join(G, "prof_r1_drain2.ncu-rep"),
+             "3. The drain regime: two-particle trajectories, fewer than fill the GPU",
+             "NS=2 M=30000 STEPS=32768 MODES=fast ncu --set full --clock-control none --import-source on "
+             "-k regex:k_integrate_thread -c 2 python scripts/bench_bins.py")
 metric_table(os.path.join(G, "prof_r1a.ncu-rep"), "4. Before the Turbo arithmetic and the hybrid kernels (same full-occupancy benchmark, earlier in the round)",
              "NS=4,16 MODES=fast ncu --set full ... python scripts/bench_bins.py", keep=lambda n: "<4," in n or "warp" in n)
 P("""## Reading
 
-* `k_integrate_thread<4, Turbo>` at full occupancy is FP32-issue bound: issue slots ~80 % busy, top stall `not_selected`
-  (more eligible warps than issue slots), L2 hit > 97 %, DRAM traffic tens of MB per launch for 2.5e9 particle-steps (HBM idle:
-  state in registers, table in L1/L2). Section 4 shows the same kernel before the Turbo arithmetic: 444 SASS instructions per
-  step; now 336 (142 FFMA, 64 FMUL, 43 FADD+..., 10 MUFU, 6 LDG, 6 F2I, 6 VIMNMX).
-* achieved (full occupancy, A = 4) = (100*4 + 10*6 + 14*1.0) flops x 19.35 M warp-steps x 32 / duration = 0.51 of the
-  72.4 TFLOP/s FFMA peak measured in the same process; what is left is instruction mix (FMUL/FADD count one flop per issue
-  slot, ~20 % of the slots are the table lookup's integer/convert work and register moves).
-* `k_free_flight<Turbo>`: 26.5 instructions per particle-step (4-step unrolled), a single dependent chain per thread.
-* `k_integrate_warp<1, Fast>` of section 4 (n = 16: 13.3e9 warp instructions) is what the hybrid kernels replaced for 9..12
-  moving particles (6-10x) and what partner lists now thin out above 16.
+* Full occupancy (section 2): `k_free_flight<Turbo>` issues on 84 % of the cycles with the FMA pipe 78 % busy -- 26
+  instructions per particle-step, nothing left but the arithmetic. `k_integrate_thread<2..4, Turbo>` as cores of split
+  trajectories (grids 1345-3860): issue 69-75 %, FMA pipe 57-61 %, L2 hit > 95 %; top stall `not_selected`/`selected`
+  (more eligible warps than issue slots). DRAM traffic per launch is the records at the segment boundaries
+  (k_integrate_thread<2>, grid 3860: 326 MB read + 108 MB written for 4.2e9 warp instructions) plus first touches of the
+  6.4 MB table: HBM is idle, the bound is FP32 issue.
+* FP32 ceilings measured in the same process (`scripts/peaks.py`): 72.4 TFLOP/s with the multiplier in a uniform register
+  (`FFMA R, R, UR, R`), **45.7 TFLOP/s with three register operands** (`FFMA R, R, R, R`: the form of almost every FFMA in
+  these kernels), 55.5 TFLOP/s as packed `FFMA2`. The whole bench evaluates 36.9 TFLOP/s of the 100/41/10/14 flop model
+  over the integrate time: 0.51 of the first ceiling, 0.81 of the second.
+* `k_pool_resolve` (once per pass, one thread per slot) is the only kernel that streams the records: 1.4 GB read, 0.5 GB
+  written for 2e6 slots in 1.8 ms = 1.06 TB/s; 1-4 % of a pass.
+* Drain (section 3): one warp per scheduler or less. A step of `k_integrate_thread<2, Turbo, LOOKAHEAD>` takes ~650
+  cycles; the source page attributes 59 % of the samples to the table gather (L1 hit 50-58 %: every step touches a new
+  32-byte sector, a pair's position in the table moves ~18 bins per step) although the value is requested one step
+  ahead. What was tried against it is in DESIGN.md section 7.
+* Section 4 is history: the kernels before the Turbo arithmetic (444 SASS instructions per step at 4 particles, 336 after)
+  and the warp-per-trajectory kernel that the hybrid kernels replaced for 9-12 particles.
 """)
 open(os.path.join(ROOT, "profiles", "r1_ncu_summary.md"), "w").write("\n".join(out) + "\n")
-print("\n".join(out[:60]))
+print("\n".join(out[:40]))
