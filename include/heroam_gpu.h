@@ -92,7 +92,8 @@ typedef struct heroam_options {
   unsigned int pool_slots; /* trajectories kept in flight by heroam_gpu_run_stats (0 = 2^22)        */
   int count_work;         /* fast mode only: 1 = the integrate kernels also count in-range pair-steps
                              (heroam_run_info.inrange_steps) at ~3 % cost; exact mode always counts   */
-  int reserved[1];
+  int no_flight;          /* cross-check only: 1 = no free flight and no splitting, every moving particle is
+                             integrated in full every step (results must not change)                  */
 } heroam_options;
 
 typedef struct heroam_traj_result {

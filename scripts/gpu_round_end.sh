@@ -11,9 +11,8 @@ SMALL="--steps 2 --warmup 1 --batch 131072 --max-time 1e6 --no-cpu --exact-step 
 python bench.py $SMALL > gpurun_out/bench_small_final.json 2> /dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_final.csv \
     python bench.py $SMALL > gpurun_out/ncu_list_final.log 2>&1
-N=1000000 python scripts/trace_pool.py
-N=1000000 ncu --set full --clock-control none --import-source on -k regex:'k_integrate_thread|k_free_flight|k_pool_resolve' \
-    -s 40 -c 16 -o gpurun_out/prof_final_pool python scripts/trace_pool.py > gpurun_out/ncu_full_final.log 2>&1
-tail -2 gpurun_out/ncu_full_final.log
-compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_traced.py tests/test_gpu_sweep.py -m gpu -x -q -k "golden or argument or cli" > gpurun_out/memcheck_final.log 2>&1
-echo "memcheck rc=$?"; tail -3 gpurun_out/memcheck_final.log
+# full-occupancy capture of the hot kernels inside a pool run; the report stays on the box (tens of MB), its raw page comes back
+N=2000000 CAP=40000 ncu --set full --clock-control none -k regex:'k_integrate_thread|k_free_flight|k_pool_resolve' \
+    -s 17 -c 18 -o /tmp/prof_final_pool2 python scripts/pool_once.py > gpurun_out/ncu_full_final2.log 2>&1
+ncu -i /tmp/prof_final_pool2.ncu-rep --page raw --csv > gpurun_out/prof_final_pool2_raw.csv
+tail -2 gpurun_out/ncu_full_final2.log

@@ -594,6 +594,8 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
   if (sg.no_flight) {
     out.bin = bin_of(a);
     m.step_stop = clip(m.steps + sg.of_bin[out.bin]);
+    if (out.bin >= BIN_WARP1 && out.bin <= BIN_WARP4)  // no partner lists either: every pair is evaluated
+      for (uint32_t s = 0; s < a; ++s) v.nbr_cnt[m.first + s] = NBR_ALL;
     return out;
   }
   // (1) the whole trajectory in free flight: the longest fixed-length tier its horizon covers
@@ -788,6 +790,28 @@ __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__r
 }
 
 // ---------------------------------------------------------------------------------
+// Turbo keeps the forces scaled by kappa, which is not a power of two: a force that went out
+// to the record (F = F' / kappa, rounded) and came back (F * kappa, rounded) need not be the
+// F' the kernel held, and the state would then depend on where the segment boundaries fall.
+// The force is a function of the positions, which do round-trip exactly, so a Turbo kernel
+// rebuilds it on entry with the very operations of its step.  (The angular velocity is scaled
+// by dt/2: exact for the usual power-of-two time steps.)
+// ---------------------------------------------------------------------------------
+template <int A, class P>
+__device__ __forceinline__ void rebuild_forces(const DevView &v, const float (&r)[A][3], float (&f)[A][3]) {
+#pragma unroll
+  for (int s = 0; s < A; ++s) { f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f; }
+#pragma unroll
+  for (int j = 0; j < A - 1; ++j) {
+#pragma unroll
+    for (int k = j + 1; k < A; ++k) {
+      const PairGeom g = pair_geom<P>(v.c, r[j], r[k]);
+      pair_apply<P>(pair_scale<P>(pair_gather<P>(v, g), g.d), g, f[j], f[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // k_integrate_thread<A>: one thread per trajectory, A active particles in registers.
 //
 // LOOKAHEAD (launched only while a run drains, A <= 4): when few warps are resident nothing
@@ -818,8 +842,10 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
       ld3(p->position, r[s]);
       load_w<P>(c, p->ang_velocity, w[s]);
       load_f<P>(c, p->force, f[s]);
-      half_kick<P>(c, r[s], f[s], hk[s]);
     }
+    if (P::turbo) rebuild_forces<A, P>(v, r, f);
+#pragma unroll
+    for (int s = 0; s < A; ++s) half_kick<P>(c, r[s], f[s], hk[s]);
     uint32_t steps = m.steps;
     float time = m.time;
     bool met = false;
@@ -954,6 +980,7 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_hybrid(DevView v, const 
       ld3(p->position, r[s]);
       load_f<P>(c, p->force, f[s]);
     }
+    if (P::turbo) rebuild_forces<A, P>(v, r, f);
     uint32_t steps = m.steps;
     float time = m.time;
     bool met = false;
@@ -1065,6 +1092,56 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_smem(DevView v, const ui
       COL(ww, s) = make_float4(w0[0], w0[1], w0[2], 0.0f);
       COL(frc, s) = make_float4(f0[0], f0[1], f0[2], 0.0f);
     }
+    // All pairs in the reference's (j,k) order: adds the pair forces of the positions in `pos` to
+    // the accumulators in `frc` (whose xyz must be zero on entry).
+    auto pair_pass = [&](float &dmin, uint32_t &in_step) {
+      for (uint32_t j = 0; j + 1 < a; ++j) {
+      const float4 rj4 = COL(pos, j);
+      float4 fj4 = COL(frc, j);
+      const float rj[3] = {rj4.x, rj4.y, rj4.z};
+      float fj[3] = {fj4.x, fj4.y, fj4.z};
+      // partners four at a time: all loads, then geometry and gathers, then the ordered
+      // accumulation, then all stores -- so that four pairs are in flight together
+      for (uint32_t k0 = j + 1; k0 < a; k0 += 4) {
+        float4 rk4[4], fk4[4];
+        PairGeom g[4];
+        float tv[4];
+        bool valid[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          valid[u] = k0 + u < a;
+          const uint32_t kk = valid[u] ? k0 + u : a - 1u;
+          rk4[u] = COL(pos, kk);
+          fk4[u] = COL(frc, kk);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float rk[3] = {rk4[u].x, rk4[u].y, rk4[u].z};
+          g[u] = pair_geom<P>(c, rj, rk);
+          if (!valid[u]) { g[u].bin = (unsigned)c.grid_len; g[u].inside = false; }  // the zero entry
+          tv[u] = pair_gather<P>(v, g[u]);
+          dmin = fminf(dmin, valid[u] ? g[u].d : 3.0e38f);
+          if (P::count) in_step += g[u].inside ? 1u : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float fk[3] = {fk4[u].x, fk4[u].y, fk4[u].z};
+          pair_apply<P>(pair_scale<P>(tv[u], g[u].d), g[u], fj, fk);  // an invalid slot adds +-0 to fj
+          fk4[u] = make_float4(fk[0], fk[1], fk[2], fk4[u].w);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (valid[u]) COL(frc, k0 + u) = fk4[u];
+      }
+      COL(frc, j) = make_float4(fj[0], fj[1], fj[2], fj4.w);
+    }
+    };
+    if (P::turbo) {  // rebuild the scaled forces from the positions (see rebuild_forces)
+      for (uint32_t s = 0; s < a; ++s) COL(frc, s) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      float dmin_unused = 3.0e38f;
+      uint32_t in_unused = 0;
+      pair_pass(dmin_unused, in_unused);
+    }
     uint32_t steps = m.steps;
     float time = m.time;
     bool met = false;
@@ -1088,46 +1165,7 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_smem(DevView v, const ui
       // all pairs, (j,k) order
       float dmin = 3.0e38f;
       uint32_t in_step = 0;
-      for (uint32_t j = 0; j + 1 < a; ++j) {
-        const float4 rj4 = COL(pos, j);
-        float4 fj4 = COL(frc, j);
-        const float rj[3] = {rj4.x, rj4.y, rj4.z};
-        float fj[3] = {fj4.x, fj4.y, fj4.z};
-        // partners four at a time: all loads, then geometry and gathers, then the ordered
-        // accumulation, then all stores -- so that four pairs are in flight together
-        for (uint32_t k0 = j + 1; k0 < a; k0 += 4) {
-          float4 rk4[4], fk4[4];
-          PairGeom g[4];
-          float tv[4];
-          bool valid[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            valid[u] = k0 + u < a;
-            const uint32_t kk = valid[u] ? k0 + u : a - 1u;
-            rk4[u] = COL(pos, kk);
-            fk4[u] = COL(frc, kk);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float rk[3] = {rk4[u].x, rk4[u].y, rk4[u].z};
-            g[u] = pair_geom<P>(c, rj, rk);
-            if (!valid[u]) { g[u].bin = (unsigned)c.grid_len; g[u].inside = false; }  // the zero entry
-            tv[u] = pair_gather<P>(v, g[u]);
-            dmin = fminf(dmin, valid[u] ? g[u].d : 3.0e38f);
-            if (P::count) in_step += g[u].inside ? 1u : 0u;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float fk[3] = {fk4[u].x, fk4[u].y, fk4[u].z};
-            pair_apply<P>(pair_scale<P>(tv[u], g[u].d), g[u], fj, fk);  // an invalid slot adds +-0 to fj
-            fk4[u] = make_float4(fk[0], fk[1], fk[2], fk4[u].w);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (valid[u]) COL(frc, k0 + u) = fk4[u];
-        }
-        COL(frc, j) = make_float4(fj[0], fj[1], fj[2], fj4.w);
-      }
+      pair_pass(dmin, in_step);
       if (dmin < c.icd2) { met = true; break; }
       // second half kick
 #pragma unroll 2
@@ -1231,27 +1269,9 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count, b
   // pairs evaluated per step (each listed pair sits in two lists)
   const unsigned long long evaluated = listed ? __reduce_add_sync(0xffffffffu, my_pairs) / 2u
                                               : (unsigned long long)a * (a - 1) / 2;
-  uint32_t steps = m.steps;
-  float time = m.time;
-  bool met = false;
-  unsigned long long inrange_total = 0;
-  while (steps < m.step_stop) {
-    const bool rn = renorm_at<P>(steps);  // one trajectory per warp: uniform
-#pragma unroll
-    for (int i = 0; i < PPL; ++i) {
-      if (own[i]) {
-        r_old[i][0] = r[i][0]; r_old[i][1] = r[i][1]; r_old[i][2] = r[i][2];
-        wh[i][0] = P::add(w[i][0], hk[i][0]);
-        wh[i][1] = P::add(w[i][1], hk[i][1]);
-        wh[i][2] = P::add(w[i][2], hk[i][2]);
-        drift<P>(c, wh[i], q[i], r[i], rn);
-        pos[lane + 32u * i] = make_float4(r[i][0], r[i][1], r[i][2], 0.0f);
-      }
-      f[i][0] = 0.0f; f[i][1] = 0.0f; f[i][2] = 0.0f;
-    }
-    __syncwarp();
-    float dmin = 3.0e38f;
-    uint32_t in_step = 0;
+  // Every lane adds to f[i] the forces of the (listed) partners of its particles, positions taken
+  // from `pos`; f[i] must be zero on entry.
+  auto partner_pass = [&](float &dmin, uint32_t &in_step) {
     // partners in ascending order, four at a time: geometry and gathers first, then the
     // (ordered) accumulation; everything branch-free, invalid slots contribute zero.
     // With partner lists (the usual case) slot k of the loop is the k-th listed partner of
@@ -1293,6 +1313,44 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count, b
           pair_apply_own<P>(pair_scale<P>(tv[u][i], dsafe), g[u][i], f[i]);
         }
     }
+  };
+  if (P::turbo) {  // rebuild the scaled forces from the positions (see rebuild_forces)
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      if (own[i]) pos[lane + 32u * i] = make_float4(r[i][0], r[i][1], r[i][2], 0.0f);
+      f[i][0] = 0.0f; f[i][1] = 0.0f; f[i][2] = 0.0f;
+    }
+    __syncwarp();
+    float dmin_unused = 3.0e38f;
+    uint32_t in_unused = 0;
+    partner_pass(dmin_unused, in_unused);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < PPL; ++i)
+      if (own[i]) half_kick<P>(c, r[i], f[i], hk[i]);
+  }
+  uint32_t steps = m.steps;
+  float time = m.time;
+  bool met = false;
+  unsigned long long inrange_total = 0;
+  while (steps < m.step_stop) {
+    const bool rn = renorm_at<P>(steps);  // one trajectory per warp: uniform
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      if (own[i]) {
+        r_old[i][0] = r[i][0]; r_old[i][1] = r[i][1]; r_old[i][2] = r[i][2];
+        wh[i][0] = P::add(w[i][0], hk[i][0]);
+        wh[i][1] = P::add(w[i][1], hk[i][1]);
+        wh[i][2] = P::add(w[i][2], hk[i][2]);
+        drift<P>(c, wh[i], q[i], r[i], rn);
+        pos[lane + 32u * i] = make_float4(r[i][0], r[i][1], r[i][2], 0.0f);
+      }
+      f[i][0] = 0.0f; f[i][1] = 0.0f; f[i][2] = 0.0f;
+    }
+    __syncwarp();
+    float dmin = 3.0e38f;
+    uint32_t in_step = 0;
+    partner_pass(dmin, in_step);
     __syncwarp();
     if (__any_sync(0xffffffffu, dmin < c.icd2)) { met = true; break; }
 #pragma unroll

@@ -493,6 +493,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     Segments sg = make_segments(ctx->opt.segment_steps, draining, split_window_max(ctx));
     sg.free_stride = ctx->free_stride;
+    sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
     k_pool_resolve<R, H><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
                                                      ctx->d_free_list);
     CU(cudaGetLastError());

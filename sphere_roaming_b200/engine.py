@@ -68,7 +68,7 @@ class Options(C.Structure):
         ("wide_kernel", C.c_int),
         ("pool_slots", C.c_uint),
         ("count_work", C.c_int),
-        ("reserved", C.c_int * 1),
+        ("no_flight", C.c_int),
     ]
 
 
@@ -183,7 +183,7 @@ class Engine:
     """One GPU context (``heroam_gpu_create``): force table resident on the device."""
 
     def __init__(self, conf: Config, table: np.ndarray, device: int = 0, mode="exact", segment_steps: int = 0,
-                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0):
+                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0, no_flight: int = 0):
         self.lib = load_library()
         self.conf = conf
         table = np.ascontiguousarray(table, dtype=np.float32)
@@ -196,6 +196,7 @@ class Engine:
         opt.wide_kernel = wide_kernel
         opt.pool_slots = pool_slots
         opt.count_work = count_work
+        opt.no_flight = no_flight
         h = C.c_void_p()
         self._check(self.lib.heroam_gpu_create(C.byref(conf), table.ctypes.data_as(C.POINTER(C.c_float)), device,
                                                C.byref(opt), C.byref(h)))

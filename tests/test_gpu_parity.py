@@ -165,6 +165,26 @@ def test_fast_mode_within_stated_tolerance(need_gpu, port, table, mode):
     assert np.allclose(np.linalg.norm(got["position"].astype(np.float64), axis=1), R, rtol=3e-6)
 
 
+@pytest.mark.parametrize("mode", ["fast", "fast_relaxed", "exact"])
+def test_free_flight_and_splitting_change_nothing(need_gpu, table, mode):
+    """The shortcuts (whole-trajectory free flight, loners split off, partner lists) against the
+    same kernels with the shortcuts switched off: every record identical, in every mode -- the
+    fast modes have no bitwise oracle, but they must at least not depend on the schedule."""
+    n, max_time = 8192, 6.0e4
+    conf = make_config(number=n, max_time=max_time)
+    with engine.Engine(conf, table, mode=mode) as eng:
+        counts, init = eng.sample(HE, n)
+        with_flight, res_a = eng.simulate(HE, counts, init)
+        info = eng.run_info()
+    with engine.Engine(conf, table, mode=mode, no_flight=1, segment_steps=1000) as eng:
+        without, res_b = eng.simulate(HE, counts, init)
+        info_b = eng.run_info()
+    assert info["free_steps"] > 0.1 * info["particle_steps"] and info_b["free_steps"] == 0
+    assert np.array_equal(res_a, res_b)
+    assert with_flight.tobytes() == without.tobytes()
+    assert info["particle_steps"] == info_b["particle_steps"] and info["pair_steps"] == info_b["pair_steps"]
+
+
 def test_gpu_sampler_matches_oracle_twin(need_gpu, port, table):
     """The Philox sampling kernel against its CPU twin: counts and geometry bit-exact,
     speeds within a few float ulps (device vs glibc log/sin/cos in double)."""
