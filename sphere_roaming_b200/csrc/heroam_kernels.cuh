@@ -742,51 +742,72 @@ __global__ void k_resolve_and_bin(DevView v, Segments sg, uint32_t step_cap, uin
 // loners of a split trajectory (act slots >= n_active; they fly [loner_from, loner_until)).
 // TrajMeta is only read, and only fields no concurrent core kernel changes.
 // ---------------------------------------------------------------------------------
+struct Flyer {
+  heroam_particle *p;
+  float q[4], w[3], w_rec[3], time;
+  uint32_t from, until;
+};
+
+template <class P>
+__device__ __forceinline__ void load_flyer(const DevView &v, const uint2 e, Flyer &fl) {
+  const TrajMeta *m = v.meta + e.x;
+  const uint32_t first = m->first;
+  const bool loner = m->n_loners != 0u;  // whole-trajectory flights have none
+  fl.from = loner ? m->loner_from : m->steps;
+  fl.until = loner ? m->loner_until : m->step_stop;
+  fl.time = loner ? m->loner_time0 : m->time;
+  fl.p = v.particles + first + v.act[first + e.y];
+  fl.q[0] = fl.p->orientation[0]; fl.q[1] = fl.p->orientation[1];
+  fl.q[2] = fl.p->orientation[2]; fl.q[3] = fl.p->orientation[3];
+  ld3(fl.p->ang_velocity, fl.w_rec);
+  load_w<P>(v.c, fl.w_rec, fl.w);
+}
+
+template <class P>
+__device__ __forceinline__ void fly_alone(const Consts &c, Flyer &fl) {
+  uint32_t k = fl.from;
+  if (P::renorm_every > 1u) {
+    // renormalisation after every renorm_every-th absolute step: single steps up to the next
+    // boundary, then whole blocks without any test, then the remainder
+    for (; k < fl.until && (k & (P::renorm_every - 1u)) != 0u; ++k) {
+      advance_orientation<P>(c, fl.w, fl.q, renorm_at<P>(k));
+      fl.time = __fadd_rn(fl.time, c.dt);
+    }
+    for (; k + P::renorm_every <= fl.until; k += P::renorm_every) {
+#pragma unroll
+      for (uint32_t u = 0; u < P::renorm_every; ++u) {
+        advance_orientation<P>(c, fl.w, fl.q, u + 1u == P::renorm_every);
+        fl.time = __fadd_rn(fl.time, c.dt);
+      }
+    }
+  }
+  for (; k < fl.until; ++k) {
+    advance_orientation<P>(c, fl.w, fl.q, renorm_at<P>(k));
+    fl.time = __fadd_rn(fl.time, c.dt);
+  }
+}
+
+template <class P>
+__device__ __forceinline__ void land_flyer(const Consts &c, const Flyer &fl) {
+  float r[3], vel[3], v2;
+  pole_position<P>(c, fl.q, r);
+  stored_velocity<P>(r, fl.w_rec, vel, v2);
+  heroam_particle *p = fl.p;
+  p->orientation[0] = fl.q[0]; p->orientation[1] = fl.q[1]; p->orientation[2] = fl.q[2]; p->orientation[3] = fl.q[3];
+  st3(p->position, r);
+  st3(p->velocity, vel);
+  p->velocity_sq = v2;
+  p->time = fl.time;
+}
+
 template <class P>
 __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__restrict__ list, uint32_t count) {
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= count) return;
-  const Consts &c = v.c;
-  const uint2 e = list[item];
-  const TrajMeta *m = v.meta + e.x;
-  const uint32_t first = m->first;
-  const bool loner = m->n_loners != 0u;  // whole-trajectory flights have none
-  const uint32_t from = loner ? m->loner_from : m->steps;
-  const uint32_t until = loner ? m->loner_until : m->step_stop;
-  float time = loner ? m->loner_time0 : m->time;
-  heroam_particle *p = v.particles + first + v.act[first + e.y];
-  float q[4] = {p->orientation[0], p->orientation[1], p->orientation[2], p->orientation[3]};
-  float w[3], w_rec[3];
-  ld3(p->ang_velocity, w_rec);
-  load_w<P>(c, w_rec, w);
-  uint32_t k = from;
-  if (P::renorm_every > 1u) {
-    // renormalisation after every renorm_every-th absolute step: single steps up to the next
-    // boundary, then whole blocks without any test, then the remainder
-    for (; k < until && (k & (P::renorm_every - 1u)) != 0u; ++k) {
-      advance_orientation<P>(c, w, q, renorm_at<P>(k));
-      time = __fadd_rn(time, c.dt);
-    }
-    for (; k + P::renorm_every <= until; k += P::renorm_every) {
-#pragma unroll
-      for (uint32_t u = 0; u < P::renorm_every; ++u) {
-        advance_orientation<P>(c, w, q, u + 1u == P::renorm_every);
-        time = __fadd_rn(time, c.dt);
-      }
-    }
-  }
-  for (; k < until; ++k) {
-    advance_orientation<P>(c, w, q, renorm_at<P>(k));
-    time = __fadd_rn(time, c.dt);
-  }
-  float r[3], vel[3], v2;
-  pole_position<P>(c, q, r);
-  stored_velocity<P>(r, w_rec, vel, v2);
-  p->orientation[0] = q[0]; p->orientation[1] = q[1]; p->orientation[2] = q[2]; p->orientation[3] = q[3];
-  st3(p->position, r);
-  st3(p->velocity, vel);
-  p->velocity_sq = v2;
-  p->time = time;
+  Flyer fl;
+  load_flyer<P>(v, list[item], fl);
+  fly_alone<P>(v.c, fl);
+  land_flyer<P>(v.c, fl);
 }
 
 // ---------------------------------------------------------------------------------
