@@ -48,6 +48,7 @@ static int h5fail(const char *fmt, ...) {
 typedef struct {
   unsigned char *p;
   size_t n, cap;
+  int oom; /* an append could not get memory: the buffer is incomplete and must not be written */
 } bytes;
 
 static int reserve_bytes(bytes *b, size_t extra) {
@@ -55,7 +56,10 @@ static int reserve_bytes(bytes *b, size_t extra) {
   size_t cap = b->cap ? b->cap * 2 : 1024;
   while (cap < b->n + extra) cap *= 2;
   unsigned char *q = (unsigned char *)realloc(b->p, cap);
-  if (!q) return -1;
+  if (!q) {
+    b->oom = 1;
+    return -1;
+  }
   b->p = q;
   b->cap = cap;
   return 0;
@@ -170,12 +174,14 @@ static void msg_begin(ohdr *h, unsigned type, unsigned flags) {
 }
 static void msg_end(ohdr *h) {
   pad8(h->b);
+  if (h->b->oom) return;
   const size_t size = h->b->n - h->msg_head - 8;
   h->b->p[h->msg_head + 2] = (unsigned char)size;
   h->b->p[h->msg_head + 3] = (unsigned char)(size >> 8);
   h->nmsg++;
 }
 static void ohdr_end(ohdr *h) {
+  if (h->b->oom) return;
   const size_t size = h->b->n - h->start - 16;
   unsigned char *p = h->b->p + h->start;
   p[2] = (unsigned char)h->nmsg;
@@ -290,6 +296,7 @@ static void build_step_template(heroam_h5_writer *w, unsigned no) {
   msg_end(&h);
   ohdr_end(&h);
   w->off_data = b->n;
+  if (b->oom) return;
   /* relative addresses, to be rebased per step */
   poke_u64(b->p + g_btree_at, w->off_btree);  w->fix[w->n_fix++] = g_btree_at;
   poke_u64(b->p + g_heap_at, w->off_heap);    w->fix[w->n_fix++] = g_heap_at;
@@ -334,7 +341,13 @@ int heroam_h5_save_timestep(heroam_h5_writer *w, unsigned int step, const heroam
         if (w->ent[i].step == step) return h5fail("step %u written twice", step);
     }
   }
-  if (no != w->tmpl_no) build_step_template(w, no);
+  if (no != w->tmpl_no) {
+    build_step_template(w, no);
+    if (w->tmpl.oom) {
+      w->failed = 1;
+      return h5fail("out of memory");
+    }
+  }
   const size_t data_bytes = (size_t)no * sizeof(heroam_particle);
   const size_t block = w->tmpl.n + ((data_bytes + 7) & ~(size_t)7);
   if (block > w->scratch_cap) {
@@ -382,10 +395,10 @@ typedef struct {
 int heroam_h5_close(heroam_h5_writer *w) {
   if (!w) return -1;
   int rc = w->failed ? -1 : 0;
-  bytes b = {0, 0, 0};
+  bytes b = {0, 0, 0, 0};
   /* root name heap: "" at offset 0, then the group names in B-tree (strcmp) order */
   qsort(w->ent, w->n_ent, sizeof *w->ent, by_name);
-  bytes names = {0, 0, 0};
+  bytes names = {0, 0, 0, 0};
   put_zero(&names, 8);
   for (size_t i = 0; i < w->n_ent; ++i) {
     w->ent[i].name_off = names.n;
@@ -395,7 +408,7 @@ int heroam_h5_close(heroam_h5_writer *w) {
   size_t heap_data_at;
   const unsigned long long heap_addr = w->eof;
   local_heap_header(&b, names.n, &heap_data_at);
-  poke_u64(b.p + heap_data_at, heap_addr + 32);
+  if (!b.oom) poke_u64(b.p + heap_data_at, heap_addr + 32);
   put(&b, names.p, names.n);
   /* symbol nodes, 2*LEAF_K entries each */
   const size_t per_snod = 2 * LEAF_K, per_node = 2 * INTERNAL_K;
@@ -446,10 +459,11 @@ int heroam_h5_close(heroam_h5_writer *w) {
   }
   free(child);
   free(parent);
+  if (b.oom || names.oom) rc = -1;
   if (rc == 0 && fwrite(b.p, 1, b.n, w->f) != b.n) rc = -1;
   w->eof += b.n;
   /* superblock v0 + root group header at offset 0 */
-  bytes s = {0, 0, 0};
+  bytes s = {0, 0, 0, 0};
   static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', 0x0d, 0x0a, 0x1a, 0x0a};
   put(&s, sig, 8);
   put_u8(&s, 0); put_u8(&s, 0); put_u8(&s, 0); put_u8(&s, 0); /* superblock, free space, root group, reserved */
@@ -463,8 +477,11 @@ int heroam_h5_close(heroam_h5_writer *w) {
   symbol_entry(&s, 0, SUPERBLOCK_BYTES, 1, root_btree, heap_addr);
   size_t bt_at, hp_at;
   group_header(&s, &bt_at, &hp_at);
-  poke_u64(s.p + bt_at, root_btree);
-  poke_u64(s.p + hp_at, heap_addr);
+  if (!s.oom) {
+    poke_u64(s.p + bt_at, root_btree);
+    poke_u64(s.p + hp_at, heap_addr);
+  }
+  if (s.oom) rc = -1;
   if (rc == 0 && (fseek(w->f, 0, SEEK_SET) != 0 || fwrite(s.p, 1, s.n, w->f) != s.n)) rc = -1;
   if (fclose(w->f) != 0) rc = -1;
   if (rc) h5fail("could not finish the HDF5 file");

@@ -153,6 +153,8 @@ static int make_consts(const heroam_config &conf, unsigned long long he_number, 
   return HEROAM_OK;
 }
 
+static int init_context(heroam_ctx *ctx, const float *force_list);
+
 extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_list, int device,
                                  const heroam_options *opt, heroam_ctx **out) {
   if (!conf || !force_list || !out) return fail(HEROAM_E_ARG, "heroam_gpu_create: null argument");
@@ -168,18 +170,30 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   if (prop.major < 10)
     return fail(HEROAM_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                 prop.major, prop.minor);
+  heroam_options options;
+  memset(&options, 0, sizeof options);
+  if (opt) options = *opt;
+  if (options.mode != HEROAM_MODE_EXACT && options.mode != HEROAM_MODE_FAST && options.mode != HEROAM_MODE_FAST_PLAIN &&
+      options.mode != HEROAM_MODE_FAST_RELAXED)
+    return fail(HEROAM_E_ARG, "unknown mode %d", options.mode);
   heroam_ctx *ctx = new heroam_ctx();
   ctx->device = device;
   ctx->conf = *conf;
-  memset(&ctx->opt, 0, sizeof ctx->opt);
-  if (opt) ctx->opt = *opt;
-  if (ctx->opt.mode != HEROAM_MODE_EXACT && ctx->opt.mode != HEROAM_MODE_FAST && ctx->opt.mode != HEROAM_MODE_FAST_PLAIN &&
-      ctx->opt.mode != HEROAM_MODE_FAST_RELAXED) {
-    delete ctx;
-    return fail(HEROAM_E_ARG, "unknown mode %d", opt->mode);
-  }
-  if (ctx->opt.segment_steps == 0) ctx->opt.segment_steps = 8192;
+  ctx->opt = options;
   ctx->sm_count = prop.multiProcessorCount;
+  const int rc = init_context(ctx, force_list);
+  if (rc) {  // whatever was created so far is released; the error message stays
+    heroam_gpu_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return HEROAM_OK;
+}
+
+// streams, events, the force table and the small fixed buffers of a context
+static int init_context(heroam_ctx *ctx, const float *force_list) {
+  const heroam_config *conf = &ctx->conf;
+  if (ctx->opt.segment_steps == 0) ctx->opt.segment_steps = 8192;
   memset(&ctx->info, 0, sizeof ctx->info);
   ctx->table_len = conf->force_grid_length;
   CU(cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking));
@@ -212,7 +226,6 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   CU(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
   CU(cudaMallocHost(&ctx->h_bin_count, N_BINS * sizeof(uint32_t)));
   CU(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
-  *out = ctx;
   return HEROAM_OK;
 }
 
