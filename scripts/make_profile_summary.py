@@ -101,7 +101,8 @@ P("""## Reading
   6.4 MB table: HBM is idle, the bound is FP32 issue.
 * FP32 ceilings measured in the same process (`scripts/peaks.py`): 72.4 TFLOP/s with the multiplier in a uniform register
   (`FFMA R, R, UR, R`), **45.7 TFLOP/s with three register operands** (`FFMA R, R, R, R`: the form of almost every FFMA in
-  these kernels), 55.5 TFLOP/s as packed `FFMA2`. The whole bench evaluates 36.9 TFLOP/s of the 100/41/10/14 flop model
+  these kernels; register-bank conflicts, so it depends on the allocation -- `k_free_flight` above does better than that
+  chain), 55.5 TFLOP/s as packed `FFMA2`. The whole bench evaluates 36.9 TFLOP/s of the 100/41/10/14 flop model
   over the integrate time: 0.51 of the first ceiling, 0.81 of the second.
 * `k_pool_resolve` (once per pass, one thread per slot) is the only kernel that streams the records: 1.4 GB read, 0.5 GB
   written for 2e6 slots in 1.8 ms = 1.06 TB/s; 1-4 % of a pass.
