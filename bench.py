@@ -129,7 +129,7 @@ def pick_ref_oracle():
     return None, "port", "port"
 
 
-def cpu_run(table, max_time: float, n_traj: int, seed_offset: int = 0):
+def cpu_run(table, max_time: float, n_traj: int, seed_offset: int = 0, dynamic: bool = True):
     """n_traj trajectories of the workload on all host cores with the reference's code:
     initialize_particles (libc rand) + the OpenMP loop over simulate_particles,
     schedule(dynamic,1) (faster than the as-written static schedule on a heavy-tailed
@@ -142,7 +142,7 @@ def cpu_run(table, max_time: float, n_traj: int, seed_offset: int = 0):
         cores = max(ref.max_threads(), all_cores)
         counts, init = ref.initialize(conf, HE, table)
         t0 = time.perf_counter()
-        final = ref.simulate(conf, HE, table, counts, init, nthreads=cores, dynamic=True)
+        final = ref.simulate(conf, HE, table, counts, init, nthreads=cores, dynamic=dynamic)
         dt = time.perf_counter() - t0
     else:
         from oracle.binding import PortOracle
@@ -169,11 +169,16 @@ def reference_arm(args, table):
         ps, s, n, cores, kind, flavour = cpu_run(table, args.max_time, sample, seed_offset=k)
         tot_ps += ps; tot_s += s; tot_traj += n
     value = tot_ps / tot_s
+    # the reference's loop as written has no schedule clause (main.c:76: static); report it too, on one sample
+    ps_static, s_static, _, _, _, _ = cpu_run(table, args.max_time, sample, seed_offset=0, dynamic=False)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "trajectories_per_sec": tot_traj / tot_s,
+        "as_written_static_schedule": {"value": ps_static / s_static, "unit": UNIT,
+                                       "note": "same code with the reference's own `#pragma omp parallel for` (no schedule clause), "
+                                               "one sample; the headline uses schedule(dynamic,1), the faster of the two"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{sample} trajectories per step x {args.steps} steps, oracle/_ref '{flavour}' build "
                                    f"(reference simulation.c+vector.c unmodified, -O3 -ffast-math -funroll-loops -fopenmp), "
