@@ -109,7 +109,8 @@ P("""## Reading
 * Drain (section 3): one warp per scheduler or less. A step of `k_integrate_thread<2, Turbo, LOOKAHEAD>` takes ~650
   cycles; the source page attributes 59 % of the samples to the table gather (L1 hit 50-58 %: every step touches a new
   32-byte sector, a pair's position in the table moves ~18 bins per step) although the value is requested one step
-  ahead. What was tried against it is in DESIGN.md section 7.
+  ahead. What was tried against it is in DESIGN.md section 7; the capture shows the one-step register look-ahead, since
+  replaced by a `cp.async` L1 prefetch two steps ahead (18 % faster on a drain-dominated run).
 * Section 4 is history: the kernels before the Turbo arithmetic (444 SASS instructions per step at 4 particles, 336 after)
   and the warp-per-trajectory kernel that the hybrid kernels replaced for 9-12 particles.
 """)

@@ -402,7 +402,7 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, 
   }
   const int width = bin >= BIN_CORE ? bin - BIN_CORE : bin;  // the core of a split trajectory runs in the kernel of its size
   static const bool lookahead_on = !(getenv("HEROAM_LOOKAHEAD") && atoi(getenv("HEROAM_LOOKAHEAD")) == 0);
-  if (draining && lookahead_on && width >= 2 && width <= 4) {  // latency-bound: gather one step ahead (see k_integrate_thread)
+  if (draining && lookahead_on && width >= 2 && width <= 4) {  // latency-bound: prefetch the table two steps ahead
     if (width == 2) k_integrate_thread<2, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
     else if (width == 3) k_integrate_thread<3, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
     else k_integrate_thread<4, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);

@@ -837,15 +837,20 @@ __device__ __forceinline__ void rebuild_forces(const DevView &v, const float (&r
 //
 // LOOKAHEAD (launched only while a run drains, A <= 4): when few warps are resident nothing
 // hides the L2 round trip of the table gather, which sits in the middle of the step's
-// dependency chain (ncu: long_scoreboard 2.3 cycles per issued instruction at A = 2).  A
-// pair's table position moves smoothly (second difference << 1 bin), so the bin of the NEXT
-// step is predicted by linear extrapolation and its value loaded one step ahead; the step
-// uses it if the prediction was right (~99 %) and falls back to a normal gather otherwise.
-// Same values either way.
+// dependency chain (a pair's table position moves ~18 bins = 72 bytes per step, so every step
+// touches a new 32-byte sector and L1 does not help on its own; ncu: 59 % of a 650-cycle step).
+// A pair's table position moves smoothly (second difference ~1e-3 bin), so the position TWO
+// steps ahead is extrapolated and its sector pulled into L1 with a cp.async whose destination
+// nobody reads: no register and so no scoreboard slot is held, nothing has to be selected or
+// checked afterwards, and a wrong guess only means an ordinary miss.  A run of 1e5 trajectories
+// (all of it drain) takes 4.2 s with it, 4.65 s without, 5.1 s with the one-step look-ahead
+// into registers it replaced (DESIGN.md section 7 has the other variants).
 // ---------------------------------------------------------------------------------
 template <int A, class P, bool LOOKAHEAD = false>
 __global__ void __launch_bounds__(INTEGRATE_TPB)
 k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
+  __shared__ float prefetch_sink[LOOKAHEAD ? INTEGRATE_TPB : 1];
+  const unsigned sink_addr = (unsigned)__cvta_generic_to_shared(prefetch_sink + (LOOKAHEAD ? threadIdx.x : 0));
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long done_steps = 0, inrange_total = 0;
   if (item < count) {
@@ -871,10 +876,9 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
     float time = m.time;
     bool met = false;
     constexpr int NP = A * (A - 1) / 2;
-    float pos_prev[LOOKAHEAD ? NP + 1 : 1], tv_ahead[LOOKAHEAD ? NP + 1 : 1];
-    unsigned bin_ahead[LOOKAHEAD ? NP + 1 : 1];
+    float pos_prev[LOOKAHEAD ? NP + 1 : 1];
 #pragma unroll
-    for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) { pos_prev[i] = 0.0f; tv_ahead[i] = 0.0f; bin_ahead[i] = 0xffffffffu; }
+    for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
     while (steps < m.step_stop) {
       const bool rn = renorm_at<P>(steps);
       // first half kick + drift (simulation.c:478-490)
@@ -907,23 +911,27 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
 #pragma unroll
         for (int k = j + 1; k < A; ++k) {
           g[k] = pair_geom<P>(c, r[j], r[k]);
+          tv[k] = pair_gather<P>(v, g[k]);
           if (LOOKAHEAD) {
+            // L1 prefetch by cp.async: the sector around the table position predicted for two steps
+            // from now is copied to a dummy slot of shared memory that nobody reads; the copy passes
+            // through L1, so the ordinary gather of that step finds its sector there
             const int pi = j * A - j * (j + 1) / 2 + (k - j - 1);  // index of pair (j,k), static after unrolling
-            tv[k] = tv_ahead[pi];
-            if (g[k].bin != bin_ahead[pi]) tv[k] = pair_gather<P>(v, g[k]);  // mispredicted (or first step)
             const float pos = P::turbo ? fmaf(g[k].d, c.inv_grid, c.pos_bias) : __fmul_rn(__fsub_rn(g[k].d, c.grid_start), c.inv_grid);
-            const float guess = 2.0f * pos - pos_prev[pi];
+            const float guess = fmaf(3.0f, pos, -2.0f * pos_prev[pi]);
             pos_prev[pi] = pos;
-            bin_ahead[pi] = min((unsigned)__float2int_rz(guess), (unsigned)c.grid_len);
-            tv_ahead[pi] = __ldg((P::turbo ? v.table_k : v.table) + bin_ahead[pi]);  // consumed next step
-          } else {
-            tv[k] = pair_gather<P>(v, g[k]);
+            const unsigned at = min((unsigned)__float2int_rz(guess), (unsigned)c.grid_len);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink_addr), "l"((P::turbo ? v.table_k : v.table) + at));
           }
           dmin = fminf(dmin, g[k].d);
           if (P::count) in_step += g[k].inside ? 1u : 0u;
         }
 #pragma unroll
         for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
+      }
+      if (LOOKAHEAD) {
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 3;");
       }
       if (dmin < c.icd2) { met = true; break; }
       // second half kick (:496-509); velocity and clock fields are written at the end
@@ -938,6 +946,7 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
       ++steps;
       inrange_total += in_step;
     }
+    if (LOOKAHEAD) asm volatile("cp.async.wait_all;");
     done_steps = steps - m.steps;
     if (met) {
 #pragma unroll
