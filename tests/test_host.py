@@ -88,3 +88,27 @@ def test_cli_usage_and_errors(tmp_path):
     assert r.returncode == 1 and "Usage:" in r.stderr
     r = subprocess.run([exe, str(tmp_path / "missing.conf")], capture_output=True, text=True)
     assert r.returncode == 1 and "Error opening config file" in r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): one JSON line
+    with the contract's keys, produced by the reference's own object code on the host cores."""
+    import json
+    import subprocess
+    import sys
+
+    from oracle.binding import ref_available
+
+    if not ref_available("release") and not ref_available("strict"):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-sample", "8", "--max-time", "2e5"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "particle-steps/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"]
