@@ -1,17 +1,19 @@
 /*
- * host/heroam_h5read.c -- `h5read <filename> <time_step>`: the post-processing tool of the
- * reference (reader.c:65-228) on top of host/heroam_h5.c instead of libhdf5.
+ * host/heroam_h5read.c -- `h5read <filename> <time_step>`: post-processing of a per-step
+ * trajectory file, the job of the reference's second executable (reader.c:65-228), on top of
+ * host/heroam_h5.c instead of libhdf5.
  *
- *   reader.c                                   here
- *   ---------------------------------------    ----------------------------------------------
- *   open_file, H5Gget_num_objs (:74-85)        heroam_h5_open, heroam_h5_num_steps
- *   read_timestep_from_hdf5 per step (:88-100) heroam_h5_read_timestep
- *   radius = |position of particle 0, step 0|  same (:104-109)
- *   trajectory_<p>.bin: float32 x,y,z / radius same bytes (:123-147)
- *   one gnuplot process per plotted step       images/step_%010llu.gp, the same commands written
- *   piping the splot command (:185-222)        to a script; run through `gnuplot` when it is on PATH
+ * Same command line, same products:
+ *   trajectory_<p>.bin        per particle, one float32 triple per time step: position divided by
+ *                             |position of particle 0 at step 0|   (reader.c:104-147, byte-identical)
+ *   images/step_%010llu.png   one frame every <time_step> steps: unit sphere with a 20 x 20 graticule,
+ *                             each particle's path so far as a line and its current place as a dot
+ *                             (reader.c:150-222)
  *
- * Like the reference it assumes every step holds the same number of particles as step 0.
+ * Built differently from the reference: the file is streamed step by step (memory is one step, not the
+ * whole file), and the frames are drawn by ONE gnuplot script with a loop (images/frames.gp) instead of
+ * one gnuplot process per frame.  gnuplot is not part of this image: the script is always written and
+ * only run when a gnuplot binary is on PATH.
  */
 #include <math.h>
 #include <stdio.h>
@@ -22,136 +24,128 @@
 
 #include "heroam_h5.h"
 
-#define PI 3.14159265358979323846
-#define N_LAT 20
-#define N_LON 20
+static double seconds_since(clock_t t0) { return (double)(clock() - t0) / CLOCKS_PER_SEC; }
 
-static void setup_gnuplot(FILE *g) { /* reader.c:14-30 */
+/* Pass over the file: normalised positions of every particle, appended step by step. */
+static int export_positions(heroam_h5_reader *file, long n_steps, unsigned *n_particles_out) {
+  FILE **out = NULL;
+  unsigned n_particles = 0;
+  double radius = 1.0;
+  int rc = 0;
+  for (long t = 0; t < n_steps && rc == 0; ++t) {
+    heroam_particles step;
+    if (heroam_h5_read_timestep(file, (unsigned)t, &step) < 0) {
+      fprintf(stderr, "Error reading timestep %llu\n", (unsigned long long)t);
+      rc = 1;
+      break;
+    }
+    if (t == 0) {
+      if (step.no == 0) {
+        fprintf(stderr, "No particle data in the first step.\n");
+        free(step.particle);
+        return 1;
+      }
+      const float *p = step.particle[0].position; /* float sum, then a double square root: reader.c:106-109 */
+      radius = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+      n_particles = step.no;
+      out = (FILE **)calloc(n_particles, sizeof *out);
+      for (unsigned k = 0; out && k < n_particles; ++k) {
+        char name[64];
+        snprintf(name, sizeof name, "trajectory_%u.bin", k);
+        out[k] = fopen(name, "wb");
+        if (!out[k]) fprintf(stderr, "Error creating file for particle %u\n", k);
+      }
+      if (!out) rc = 1;
+    }
+    /* like the reference, every step is expected to hold the particles of step 0 */
+    for (unsigned k = 0; rc == 0 && k < n_particles && k < step.no; ++k) {
+      if (!out[k]) continue;
+      const float *p = step.particle[k].position;
+      const float unit[3] = {(float)(p[0] / radius), (float)(p[1] / radius), (float)(p[2] / radius)};
+      if (fwrite(unit, sizeof unit, 1, out[k]) != 1) rc = 1;
+    }
+    free(step.particle);
+  }
+  for (unsigned k = 0; out && k < n_particles; ++k)
+    if (out[k]) fclose(out[k]);
+  free(out);
+  *n_particles_out = n_particles;
+  return rc;
+}
+
+/* The graticule as inline data: parallels every 9 degrees, meridians every 18. */
+static void graticule(FILE *g) {
+  const double pi = acos(-1.0);
+  const int n = 20;
+  fprintf(g, "$parallels << EOD\n");
+  for (int k = 1; k < n; ++k) {
+    const double polar = pi * k / n;
+    for (int j = 0; j <= n; ++j) fprintf(g, "%f %f %f\n", sin(polar) * cos(2 * pi * j / n), sin(polar) * sin(2 * pi * j / n), cos(polar));
+    fprintf(g, "\n");
+  }
+  fprintf(g, "EOD\n$meridians << EOD\n");
+  for (int j = 0; j < n; ++j) {
+    for (int k = 0; k <= n; ++k) fprintf(g, "%f %f %f\n", sin(pi * k / n) * cos(2 * pi * j / n), sin(pi * k / n) * sin(2 * pi * j / n), cos(pi * k / n));
+    fprintf(g, "\n");
+  }
+  fprintf(g, "EOD\n");
+}
+
+static int write_frames_script(const char *path, long n_steps, int every, unsigned n_particles) {
+  FILE *g = fopen(path, "w");
+  if (!g) return 1;
+  fprintf(g, "# frames of h5read: gnuplot %s\n", path);
   fprintf(g, "set terminal pngcairo enhanced size 800,800\n");
-  fprintf(g, "unset border\nunset key\nset xzeroaxis\nset yzeroaxis\nset zzeroaxis\nset xyplane at 0\nunset tics\n");
-  fprintf(g, "set parametric\nset xrange [-1.2:1.2]\nset yrange [-1.2:1.2]\nset zrange [-1.2:1.2]\n");
-  fprintf(g, "set view equal xyz\nset size ratio -1\nset autoscale fix\n");
+  fprintf(g, "unset border; unset key; unset tics\n");
+  fprintf(g, "set xzeroaxis; set yzeroaxis; set zzeroaxis; set xyplane at 0\n");
+  fprintf(g, "set xrange [-1.2:1.2]; set yrange [-1.2:1.2]; set zrange [-1.2:1.2]\n");
+  fprintf(g, "set view equal xyz; set size ratio -1\n");
+  fprintf(g, "colour(p) = word('#007ACC #FF4500 #32CD32 #FFD700 #8A2BE2 #FF69B4 #40E0D0 #DC143C #6495ED #FF8C00', p %% 10 + 1)\n");
+  fprintf(g, "path(p) = sprintf('trajectory_%%d.bin', p)\n");
+  graticule(g);
+  fprintf(g, "do for [t = 0:%ld:%d] {\n", n_steps - 1, every);
+  fprintf(g, "  set output sprintf('images/step_%%010d.png', t)\n");
+  fprintf(g, "  set title sprintf('Time %%d fs', t)\n");
+  fprintf(g, "  splot $parallels w l lc 'gray', $meridians w l lc 'gray', \\\n");
+  fprintf(g, "    for [p = 0:%u] path(p) binary format='%%float%%float%%float' every ::0::(t > 0 ? t - 1 : 0) u 1:2:3 w l lc rgb colour(p), \\\n",
+          n_particles - 1);
+  fprintf(g, "    for [p = 0:%u] path(p) binary format='%%float%%float%%float' every ::t::t u 1:2:3 w p pt 7 lc rgb colour(p)\n",
+          n_particles - 1);
+  fprintf(g, "  unset output\n}\n");
+  fclose(g);
+  return 0;
 }
-
-static void sphere_grid(FILE *g) { /* the inline data of the two '-' plots, reader.c:32-63 */
-  for (int k = 1; k < N_LAT; k++) {
-    const double theta = (PI * k) / N_LAT, z = cos(theta), r = sin(theta);
-    for (int j = 0; j <= N_LON; j++) {
-      const double phi = (2 * PI * j) / N_LON;
-      fprintf(g, "%f %f %f\n", r * cos(phi), r * sin(phi), z);
-    }
-    fprintf(g, "\n");
-  }
-  fprintf(g, "e\n");
-  for (int j = 0; j < N_LON; j++) {
-    const double phi = (2 * PI * j) / N_LON;
-    for (int k = 0; k <= N_LAT; k++) {
-      const double theta = (PI * k) / N_LAT;
-      fprintf(g, "%f %f %f\n", sin(theta) * cos(phi), sin(theta) * sin(phi), cos(theta));
-    }
-    fprintf(g, "\n");
-  }
-  fprintf(g, "e\n");
-}
-
-static int gnuplot_on_path(void) { return system("command -v gnuplot > /dev/null 2>&1") == 0; }
 
 int main(int argc, char *argv[]) {
   if (argc != 3) {
     fprintf(stderr, "Usage: %s <filename> <time_step>\n", argv[0]);
     return 1;
   }
-  const char *filename = argv[1];
-  const int plot_time_step = atoi(argv[2]);
-  heroam_h5_reader *file = heroam_h5_open(filename);
+  const int every = atoi(argv[2]);
+  heroam_h5_reader *file = heroam_h5_open(argv[1]);
   if (!file) {
-    fprintf(stderr, "Error opening HDF5 file '%s'.\n", filename);
+    fprintf(stderr, "Error opening HDF5 file '%s'.\n", argv[1]);
     return 1;
   }
-  clock_t start = clock();
-  const long num_time = heroam_h5_num_steps(file);
-  printf("Time steps in file: %llu\n", (unsigned long long)num_time);
-  heroam_particles *particles = (heroam_particles *)calloc((size_t)(num_time > 0 ? num_time : 1), sizeof *particles);
-  for (long i = 0; i < num_time; ++i) {
-    if (heroam_h5_read_timestep(file, (unsigned)i, &particles[i]) < 0) {
-      fprintf(stderr, "Error reading timestep %llu\n", (unsigned long long)i);
-      for (long j = 0; j < i; j++) free(particles[j].particle);
-      free(particles);
-      heroam_h5_reader_close(file);
-      return 1;
-    }
-  }
+  const long n_steps = heroam_h5_num_steps(file);
+  printf("Time steps in file: %llu\n", (unsigned long long)n_steps);
+  clock_t t0 = clock();
+  unsigned n_particles = 0;
+  const int failed = n_steps <= 0 || export_positions(file, n_steps, &n_particles);
   heroam_h5_reader_close(file);
-  printf("Reading time: %.2fs\n", (double)(clock() - start) / CLOCKS_PER_SEC);
-  if (num_time <= 0 || particles[0].no == 0) {
-    fprintf(stderr, "No particle data in '%s'.\n", filename);
-    free(particles);
-    return 1;
-  }
-  const unsigned int num_particles = particles[0].no;
-  const float *first_pos = particles[0].particle[0].position;
-  const double radius = sqrt(first_pos[0] * first_pos[0] + first_pos[1] * first_pos[1] + first_pos[2] * first_pos[2]);
+  if (failed) return 1;
+  printf("Trajectory write time: %.2fs\n", seconds_since(t0));
 
-  start = clock();
-#pragma omp parallel for
-  for (unsigned int p = 0; p < num_particles; p++) {
-    char name[256];
-    snprintf(name, sizeof name, "trajectory_%u.bin", p);
-    FILE *out = fopen(name, "wb");
-    if (!out) {
-      fprintf(stderr, "Error creating file for particle %u\n", p);
-      continue;
-    }
-    for (long t = 0; t < num_time; t++) {
-      if (p >= particles[t].no) break;
-      const float *pos = particles[t].particle[p].position;
-      const float normalized[3] = {(float)(pos[0] / radius), (float)(pos[1] / radius), (float)(pos[2] / radius)};
-      fwrite(normalized, sizeof(float), 3, out);
-    }
-    fclose(out);
-  }
-  printf("Trajectory write time: %.2fs\n", (double)(clock() - start) / CLOCKS_PER_SEC);
-  for (long i = 0; i < num_time; i++) free(particles[i].particle);
-  free(particles);
-
-  start = clock();
-  static const char *colors[] = {"#007ACC", "#FF4500", "#32CD32", "#FFD700", "#8A2BE2",
-                                 "#FF69B4", "#40E0D0", "#DC143C", "#6495ED", "#FF8C00"};
-  const int num_colors = (int)(sizeof colors / sizeof colors[0]);
+  t0 = clock();
   struct stat st;
   if (stat("images", &st) == -1) mkdir("images", 0700);
-  const int have_gnuplot = gnuplot_on_path();
-  if (plot_time_step > 0) {
-#pragma omp parallel for schedule(dynamic)
-    for (long t = 0; t < num_time; t += plot_time_step) {
-      char script[64];
-      snprintf(script, sizeof script, "images/step_%010llu.gp", (unsigned long long)t);
-      FILE *g = fopen(script, "w");
-      if (!g) continue;
-      setup_gnuplot(g);
-      fprintf(g, "set output 'images/step_%010llu.png'\n", (unsigned long long)t);
-      fprintf(g, "set title 'Time %llu fs'\n", (unsigned long long)t);
-      fprintf(g, "splot '-' w l lc 'gray', '-' w l lc 'gray'");
-      for (unsigned int p = 0; p < num_particles; p++) {
-        const char *color = colors[p % num_colors];
-        if (t > 0)
-          fprintf(g, ", 'trajectory_%u.bin' binary format='%%float%%float%%float' every ::0::%llu using 1:2:3 w l lc rgb '%s'",
-                  p, (unsigned long long)(t - 1), color);
-        fprintf(g, ", 'trajectory_%u.bin' binary format='%%float%%float%%float' every ::%llu::%llu using 1:2:3 w p pt 7 lc rgb '%s'",
-                p, (unsigned long long)t, (unsigned long long)t, color);
-      }
-      fprintf(g, "\n");
-      sphere_grid(g);
-      fprintf(g, "unset output\n");
-      fclose(g);
-      if (have_gnuplot) {
-        char cmd[128];
-        snprintf(cmd, sizeof cmd, "gnuplot %s", script);
-        if (system(cmd) != 0) fprintf(stderr, "gnuplot failed for timestep %llu\n", (unsigned long long)t);
-      }
+  if (every > 0 && write_frames_script("images/frames.gp", n_steps, every, n_particles) == 0) {
+    if (system("command -v gnuplot > /dev/null 2>&1") == 0) {
+      if (system("gnuplot images/frames.gp") != 0) fprintf(stderr, "gnuplot failed on images/frames.gp\n");
+    } else {
+      printf("gnuplot is not on PATH: run `gnuplot images/frames.gp` where it is\n");
     }
   }
-  if (!have_gnuplot) printf("gnuplot is not on PATH: wrote images/step_*.gp, render them with `gnuplot <script>`\n");
-  printf("Total plotting time: %.2fs\n", (double)(clock() - start) / CLOCKS_PER_SEC);
+  printf("Total plotting time: %.2fs\n", seconds_since(t0));
   return 0;
 }

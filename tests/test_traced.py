@@ -102,10 +102,10 @@ def test_h5read_exports_normalised_positions(golden, tmp_path):
         got = np.fromfile(tmp_path / f"trajectory_{p}.bin", dtype="<f4").reshape(-1, 3)
         want = (snaps["position"][:, p, :].astype(np.float64) / radius).astype(np.float32)
         assert np.array_equal(got, want)
-    scripts = sorted(os.listdir(tmp_path / "images"))
-    assert [s for s in scripts if s.endswith(".gp")] == [f"step_{t:010d}.gp" for t in range(0, len(snaps), 50)]
-    text = (tmp_path / "images" / "step_0000000050.gp").read_text()
-    assert "every ::0::49 using 1:2:3 w l" in text and "every ::50::50 using 1:2:3 w p pt 7" in text
+    # the frames are drawn by one gnuplot script (gnuplot itself is not in the image)
+    text = (tmp_path / "images" / "frames.gp").read_text()
+    assert f"do for [t = 0:{len(snaps) - 1}:50]" in text and "images/step_%010d.png" in text
+    assert f"for [p = 0:{snaps.shape[1] - 1}] path(p)" in text and "$parallels << EOD" in text
     # the usage message of the reference
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 1 and "Usage:" in r.stderr
