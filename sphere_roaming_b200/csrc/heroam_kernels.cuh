@@ -301,7 +301,10 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
   // free flight: ~73 ns per step; the short tier is dropped while draining (schedule_segment)
   sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
   sg.of_bin[BIN_FREE + 1] = scaled(2, 1);
-  sg.of_bin[BIN_FREE + 2] = scaled(8, 1);
+  // While draining a pass lasts as long as its slowest kernel, and every trajectory advances one
+  // segment per pass: a long tier of 8x (65 536 steps x 73 ns = 4.8 ms for a hundred flyers) would hold
+  // up the thousands of two-particle trajectories whose segment takes half of that.
+  sg.of_bin[BIN_FREE + 2] = drain ? scaled(4, 1) : scaled(8, 1);
   // split trajectories: core and loners advance by the same fixed window.  The reach bound grows
   // with the square of the window (possible acceleration), so beyond split_window_max =
   // O(sqrt(m / f_max) / dt) everything would look linked to everything.
