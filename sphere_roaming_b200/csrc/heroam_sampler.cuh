@@ -329,6 +329,11 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
         accumulate_stats(v, m, pool.stats + m.point);
         m.status = ST_FREE;
       }
+      // Once the index space is used up there is nothing to claim.  A plain load first: the free slots
+      // (millions, late in a run) would otherwise all serialise on the cursor's atomic in every pass,
+      // ~1 ns each -- 4 ms per pass with 4e6 free slots.  The cursor only grows, so a stale value
+      // can only send a thread on to the atomic, never past a trajectory.
+      if (*reinterpret_cast<volatile unsigned long long *>(pool.cursor) >= pool.count) break;
       const unsigned long long idx = atomicAdd(pool.cursor, 1ull);
       if (idx >= pool.count) break;
       uint32_t pt = 0;
