@@ -46,7 +46,7 @@ def test_reader_parses_a_file_written_by_libhdf5():
     np.testing.assert_allclose(ds.data.ravel(), np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
 
 
-@pytest.mark.parametrize("n_steps,no", [(1, 1), (3, 4), (9, 2), (257, 5), (3000, 3)])
+@pytest.mark.parametrize("n_steps,no", [(1, 1), (3, 4), (9, 2), (257, 5), (3000, 3), (40000, 1)])  # 1..3 B-tree levels
 def test_write_then_read_back(tmp_path, n_steps, no):
     rng = np.random.default_rng(n_steps * 131 + no)
     path = str(tmp_path / "trajectory_000007.h5")
