@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define HEROAM_ABI_VERSION 1
+#define HEROAM_ABI_VERSION 2
 
 enum {
   HEROAM_OK = 0,
@@ -94,6 +94,13 @@ typedef struct heroam_options {
                              (heroam_run_info.inrange_steps) at ~3 % cost; exact mode always counts   */
   int no_flight;          /* cross-check only: 1 = no free flight and no splitting, every moving particle is
                              integrated in full every step (results must not change)                  */
+  /* The end of a run (fewer live trajectories than fill the GPU, nothing left to refill) is handed to
+   * the drain kernel: one thread owns a trajectory for a whole time slice and re-analyses, flies and
+   * integrates it on its own, instead of one segment per pass.                 */
+  int no_drain_kernel;    /* cross-check only: 1 = keep the pass-per-segment schedule to the end
+                             (results must not change)                                                 */
+  unsigned int drain_slice_us;      /* length of a drain time slice in microseconds (0 = default)     */
+  unsigned int drain_segment_steps; /* steps between re-analyses inside the drain kernel (0 = default) */
 } heroam_options;
 
 typedef struct heroam_traj_result {

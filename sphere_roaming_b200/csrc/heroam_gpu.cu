@@ -222,9 +222,9 @@ static int init_context(heroam_ctx *ctx, const float *force_list) {
   ctx->nbr_cap = 64ull << 20;
   CU(cudaMalloc(&ctx->d_nbr_pool, ctx->nbr_cap));
   CU(cudaMalloc(&ctx->d_nbr_used, sizeof(unsigned long long)));
-  CU(cudaMalloc(&ctx->d_bin_count, N_BINS * sizeof(uint32_t)));
+  CU(cudaMalloc(&ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t)));
   CU(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
-  CU(cudaMallocHost(&ctx->h_bin_count, N_BINS * sizeof(uint32_t)));
+  CU(cudaMallocHost(&ctx->h_bin_count, N_BIN_COUNTERS * sizeof(uint32_t)));
   CU(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
   return HEROAM_OK;
 }
@@ -390,11 +390,56 @@ static int refresh_scaled_table(heroam_ctx *ctx, const Consts &c) {
   return HEROAM_OK;
 }
 
-template <class P>
+// How a run is being scheduled at the moment.
+struct Regime {
+  bool draining = false;      // fewer trajectories in the full kernels than fill the GPU: latency-bound segment table
+  bool drain_kernel = false;  // nothing left to refill and the survivors fit the GPU: k_drain owns the narrow ones
+};
+
+static int env_int(const char *name, int fallback) {
+  const char *e = getenv(name);
+  return e && *e ? atoi(e) : fallback;
+}
+
+// Decide the regime of the next pass from the populations the resolve kernel just reported.
+// can_refill: free slots would still be filled with new trajectories (streaming pool).
+static void update_regime(const heroam_ctx *ctx, Regime &rg, bool can_refill) {
+  uint64_t in_kernels = 0;
+  for (int b = 1; b < N_BINS; ++b)
+    if (b < BIN_FREE || b >= BIN_CORE) in_kernels += ctx->h_bin_count[b];
+  rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
+  static const int per_sm = env_int("HEROAM_DRAIN_PER_SM", 640);
+  // the live population only shrinks from here on, so the decision is never taken back
+  if (!ctx->opt.no_drain_kernel && !ctx->opt.no_flight && !can_refill &&
+      ctx->h_bin_count[LIVE_SLOT] <= (uint64_t)ctx->sm_count * per_sm)
+    rg.drain_kernel = true;
+}
+
+// R: arithmetic of the resolve steps, P: of the integrate kernels
+template <class R, class P>
 static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, bool draining = false) {
   const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
+  if (bin > BIN_DRAIN) {
+    // one time slice of the drain: every thread runs its trajectory until the SM clock says stop
+    const unsigned slice_us = ctx->opt.drain_slice_us ? ctx->opt.drain_slice_us : 10000u;
+    const unsigned seg = ctx->opt.drain_segment_steps ? ctx->opt.drain_segment_steps : 4096u;
+    int khz = 0;
+    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device));
+    const long long budget = (long long)slice_us * (long long)khz / 1000;
+    const Segments dsg = make_drain_segments((uint32_t)seg, split_window_max(ctx));
+    const uint32_t cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)ctx->opt.max_steps;
+    const unsigned dgrid = (cnt + DRAIN_TPB - 1) / DRAIN_TPB;
+    switch (bin - BIN_DRAIN) {
+      case 1: k_drain<1, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
+      case 2: k_drain<2, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
+      case 3: k_drain<3, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
+      default: k_drain<4, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
+    }
+    CU(cudaGetLastError());
+    return HEROAM_OK;
+  }
   if (bin >= BIN_FREE && bin < BIN_CORE) {
     k_free_flight<P><<<(cnt + 127) / 128, 128, 0, s>>>(v, ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride, cnt);
     CU(cudaGetLastError());
@@ -466,22 +511,23 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
                                                                                     : (uint32_t)ctx->opt.max_steps;
   double integrate_ms = 0.0;
   bool pending_timing = false;
-  bool draining = false;
+  Regime rg;
   CU(cudaEventRecord(ctx->ev_start, ctx->main));
   CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
   k_prepare<<<tgrid, 128, 0, ctx->main>>>(v, ctx->d_first, ctx->d_counts);
   CU(cudaGetLastError());
   ctx->info.kernel_launches++;
   for (;;) {
-    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
+    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
-    Segments sg = make_segments(ctx->opt.segment_steps, draining, split_window_max(ctx));
+    Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
     sg.free_stride = ctx->free_stride;
     sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
+    sg.drain_kernel = rg.drain_kernel ? 1u : 0u;
     k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
-    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
     CU(cudaStreamSynchronize(ctx->main));
     if (pending_timing) {
       float ms = 0;
@@ -492,13 +538,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     uint64_t live = 0;
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
     if (live == 0) break;
-    {
-      uint64_t trajectories = 0;
-      for (int b = 1; b < N_BINS; ++b)
-        if (b < BIN_FREE || b >= BIN_CORE) trajectories += ctx->h_bin_count[b];
-      // fewer trajectories in the full kernels than fill the GPU once: latency-bound from here on
-      draining = trajectories < (uint64_t)ctx->sm_count * 768;
-    }
+    update_regime(ctx, rg, false);
     ctx->info.passes++;
     CU(cudaEventRecord(ctx->ev_i0, ctx->main));
     for (int b = 1; b < N_BINS; ++b) {
@@ -506,7 +546,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
       if (!cnt) continue;
       // the bin streams start after ev_i0, i.e. after this pass's resolve kernel
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<H>(ctx, v, b, cnt, draining);
+      int rc = launch_bin<R, H>(ctx, v, b, cnt, rg.draining);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
@@ -686,11 +726,11 @@ static int run_traced(heroam_ctx *ctx, const Consts &c, const uint32_t *counts, 
   bool pending = false;  // buffer cur ^ 1 is on its way to the host
   int rc = HEROAM_OK;
   for (;;) {
-    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
+    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
-    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
     CU(cudaStreamSynchronize(ctx->main));
     uint64_t live = 0;
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];

@@ -34,7 +34,15 @@ constexpr int BIN_FREE = 17;      // BIN_FREE + 0: short, + 1: medium, + 2: long
 constexpr int FREE_SPLIT = 3;     // BIN_FREE + 3: loners split off a trajectory whose core keeps interacting
 constexpr int N_FREE_TIERS = 4;
 constexpr int BIN_CORE = BIN_FREE + N_FREE_TIERS;  // BIN_CORE + a: cores of split trajectories, a = 1..8 (k_integrate_thread<a>)
-constexpr int N_BINS = BIN_CORE + 9;
+// Drain regime (fewer live trajectories than fill the GPU, nothing left to refill): k_drain<w>, one thread
+// per trajectory with at most w particles still moving, which re-analyses, flies and integrates its
+// trajectory on its own for a whole time slice instead of one segment per pass.
+constexpr int BIN_DRAIN = BIN_CORE + 9;   // BIN_DRAIN + w, w = 1..DRAIN_MAX_W
+constexpr int DRAIN_MAX_W = 4;
+constexpr int N_BINS = BIN_DRAIN + DRAIN_MAX_W + 1;
+constexpr int LIVE_SLOT = N_BINS;         // bin_count[LIVE_SLOT]: live trajectories seen by the resolve kernel
+constexpr int N_BIN_COUNTERS = N_BINS + 1;
+constexpr int DRAIN_TPB = 64;
 constexpr int FREE_MAX_A = 8;     // the free-flight analysis is done for trajectories with <= 8 moving particles
 constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
 constexpr int INTEGRATE_TPB = 128;
@@ -271,6 +279,8 @@ struct Segments {
                           // the short free-flight tier would only slow per-pass progress
   uint32_t no_flight;     // 1: per-step capture -- every particle's record must be current at every step
                           // boundary, so nobody flies and nothing is split off
+  uint32_t drain_kernel;  // 1: trajectories with <= DRAIN_MAX_W moving particles are only settled and listed by
+                          // moving count; k_drain schedules and runs them
 };
 
 __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split_window_max) {
@@ -315,6 +325,29 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
   sg.free_stride = 0;
   sg.drain = drain ? 1u : 0u;
   sg.no_flight = 0;
+  sg.drain_kernel = 0;
+  return sg;
+}
+
+// Segments the threads of k_drain schedule themselves with.  Nothing waits for anything here, so
+// lengths are chosen for the trajectory alone: re-analysis is cheap (a few hundred instructions
+// against ~100 per particle-step), so interacting segments are short -- the sooner a pair that has
+// flown apart is found out, the sooner it flies (a flight step has a quarter of the dependency
+// chain of a full step) -- and flights take the longest tier their horizon covers.
+__host__ inline Segments make_drain_segments(uint32_t base, uint32_t split_window_max) {
+  Segments sg;
+  for (int b = 0; b < N_BINS; ++b) sg.of_bin[b] = base;
+  sg.of_bin[BIN_FREE + 0] = base / 8u ? base / 8u : 1u;
+  sg.of_bin[BIN_FREE + 1] = base;
+  sg.of_bin[BIN_FREE + 2] = base * 8u;
+  uint32_t window = base;
+  while (window > split_window_max && window > 64u) window /= 2u;
+  sg.of_bin[BIN_FREE + FREE_SPLIT] = window;
+  for (int a = 0; a <= THREAD_MAX_A; ++a) sg.of_bin[BIN_CORE + a] = window;
+  sg.free_stride = 0;
+  sg.drain = 0;       // splitting and the short flight tier stay on
+  sg.no_flight = 0;
+  sg.drain_kernel = 0;
   return sg;
 }
 
@@ -325,6 +358,7 @@ __host__ inline Segments make_capture_segments(uint32_t chunk) {
   sg.free_stride = 0;
   sg.drain = 0;
   sg.no_flight = 1;
+  sg.drain_kernel = 0;
   return sg;
 }
 
@@ -667,6 +701,10 @@ __device__ inline void append_schedule(const Schedule &sc, uint32_t t, uint32_t 
                                        uint32_t free_stride) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned peers = __match_any_sync(0xffffffffu, sc.bin);
+  {  // live trajectories (anything scheduled), one atomic per warp
+    const unsigned alive = __ballot_sync(0xffffffffu, sc.bin >= 0 || sc.fly_tier >= 0);
+    if (lane == 0 && alive) atomicAdd(bin_count + LIVE_SLOT, (uint32_t)__popc(alive));
+  }
   if (sc.bin >= 0) {
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
@@ -699,19 +737,31 @@ __device__ inline void flush_work(const DevView &v, const Counters &work) {
   }
 }
 
-// One resolve visit of a live trajectory: returns what to launch for it (nothing if it ended).
+// First half of a resolve visit of a live trajectory: finish what the kernels left pending and
+// evaluate the exit.  Returns true if the trajectory is over (m.status = ST_DONE + code).
 // P: arithmetic of the meeting step; H: arithmetic of the integrate kernels (a rewound loner
 // must be re-flown exactly as k_free_flight<H> flew it).
 template <class P, class H>
-__device__ inline Schedule resolve_live(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap,
-                                        Counters &work) {
+__device__ inline bool settle_and_exit(const DevView &v, TrajMeta &m, uint32_t step_cap, Counters &work) {
   settle<P>(v, m, work);
   const uint32_t done = evaluate_exit(v.c, m, step_cap);
-  if (done != NOT_DONE) {
-    if (m.n_loners && m.loner_until > m.steps) rewind_loners<H>(v, m, work);
-    m.status = ST_DONE + done;
-    if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported += 1;
-    return Schedule();
+  if (done == NOT_DONE) return false;
+  if (m.n_loners && m.loner_until > m.steps) rewind_loners<H>(v, m, work);
+  m.status = ST_DONE + done;
+  if (done == HEROAM_DONE_UNSUPPORTED) work.unsupported += 1;
+  return true;
+}
+
+// One resolve visit of a live trajectory: returns what to launch for it (nothing if it ended).
+template <class P, class H>
+__device__ inline Schedule resolve_live(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap,
+                                        Counters &work) {
+  if (settle_and_exit<P, H>(v, m, step_cap, work)) return Schedule();
+  const uint32_t moving = m.n_active + m.n_loners;
+  if (sg.drain_kernel && !sg.no_flight && moving >= 1u && moving <= (uint32_t)DRAIN_MAX_W) {
+    Schedule out;  // k_drain does its own scheduling: only list the trajectory by its moving count
+    out.bin = BIN_DRAIN + (int)moving;
+    return out;
   }
   return schedule_segment(v, m, sg, step_cap, work);
 }
@@ -752,42 +802,58 @@ struct Flyer {
 };
 
 template <class P>
-__device__ __forceinline__ void load_flyer(const DevView &v, const uint2 e, Flyer &fl) {
-  const TrajMeta *m = v.meta + e.x;
-  const uint32_t first = m->first;
-  const bool loner = m->n_loners != 0u;  // whole-trajectory flights have none
-  fl.from = loner ? m->loner_from : m->steps;
-  fl.until = loner ? m->loner_until : m->step_stop;
-  fl.time = loner ? m->loner_time0 : m->time;
-  fl.p = v.particles + first + v.act[first + e.y];
+__device__ __forceinline__ void load_flyer(const DevView &v, const TrajMeta &m, uint32_t slot, Flyer &fl) {
+  const uint32_t first = m.first;
+  const bool loner = m.n_loners != 0u;  // whole-trajectory flights have none
+  fl.from = loner ? m.loner_from : m.steps;
+  fl.until = loner ? m.loner_until : m.step_stop;
+  fl.time = loner ? m.loner_time0 : m.time;
+  fl.p = v.particles + first + v.act[first + slot];
   fl.q[0] = fl.p->orientation[0]; fl.q[1] = fl.p->orientation[1];
   fl.q[2] = fl.p->orientation[2]; fl.q[3] = fl.p->orientation[3];
   ld3(fl.p->ang_velocity, fl.w_rec);
   load_w<P>(v.c, fl.w_rec, fl.w);
 }
 
-template <class P>
-__device__ __forceinline__ void fly_alone(const Consts &c, Flyer &fl) {
-  uint32_t k = fl.from;
+// N flyers of ONE trajectory (same from / until / clock) advanced together: their steps are
+// independent, so interleaving them hides each other's dependency chains.  Per flyer exactly
+// the operations of the full kernels, in their order.
+template <class P, int N>
+__device__ __forceinline__ void fly_together(const Consts &c, Flyer (&fl)[N]) {
+  uint32_t k = fl[0].from;
+  const uint32_t until = fl[0].until;
+  float time = fl[0].time;
   if (P::renorm_every > 1u) {
     // renormalisation after every renorm_every-th absolute step: single steps up to the next
     // boundary, then whole blocks without any test, then the remainder
-    for (; k < fl.until && (k & (P::renorm_every - 1u)) != 0u; ++k) {
-      advance_orientation<P>(c, fl.w, fl.q, renorm_at<P>(k));
-      fl.time = __fadd_rn(fl.time, c.dt);
+    for (; k < until && (k & (P::renorm_every - 1u)) != 0u; ++k) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) advance_orientation<P>(c, fl[i].w, fl[i].q, renorm_at<P>(k));
+      time = __fadd_rn(time, c.dt);
     }
-    for (; k + P::renorm_every <= fl.until; k += P::renorm_every) {
+    for (; k + P::renorm_every <= until; k += P::renorm_every) {
 #pragma unroll
       for (uint32_t u = 0; u < P::renorm_every; ++u) {
-        advance_orientation<P>(c, fl.w, fl.q, u + 1u == P::renorm_every);
-        fl.time = __fadd_rn(fl.time, c.dt);
+#pragma unroll
+        for (int i = 0; i < N; ++i) advance_orientation<P>(c, fl[i].w, fl[i].q, u + 1u == P::renorm_every);
+        time = __fadd_rn(time, c.dt);
       }
     }
   }
-  for (; k < fl.until; ++k) {
-    advance_orientation<P>(c, fl.w, fl.q, renorm_at<P>(k));
-    fl.time = __fadd_rn(fl.time, c.dt);
+  for (; k < until; ++k) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) advance_orientation<P>(c, fl[i].w, fl[i].q, renorm_at<P>(k));
+    time = __fadd_rn(time, c.dt);
   }
+#pragma unroll
+  for (int i = 0; i < N; ++i) fl[i].time = time;
+}
+
+template <class P>
+__device__ __forceinline__ void fly_alone(const Consts &c, Flyer &fl) {
+  Flyer one[1] = {fl};
+  fly_together<P, 1>(c, one);
+  fl = one[0];
 }
 
 template <class P>
@@ -808,7 +874,8 @@ __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__r
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= count) return;
   Flyer fl;
-  load_flyer<P>(v, list[item], fl);
+  const uint2 e = list[item];
+  load_flyer<P>(v, v.meta[e.x], e.y, fl);
   fly_alone<P>(v.c, fl);
   land_flyer<P>(v.c, fl);
 }
@@ -849,6 +916,120 @@ __device__ __forceinline__ void rebuild_forces(const DevView &v, const float (&r
 // (all of it drain) takes 4.2 s with it, 4.65 s without, 5.1 s with the one-step look-ahead
 // into registers it replaced (DESIGN.md section 7 has the other variants).
 // ---------------------------------------------------------------------------------
+// One segment of a trajectory with A moving particles, by one thread: loads the records, runs
+// steps [m.steps, m.step_stop) or up to a meeting, leaves the records (clean, or mid-step) and
+// updates m (steps, clock, status).  Returns the number of steps completed.
+template <int A, class P, bool LOOKAHEAD>
+__device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, TrajMeta &m, const unsigned sink_addr,
+                                                             unsigned long long &inrange_total) {
+  const Consts &c = v.c;
+  heroam_particle *rec[A];
+  float q[A][4], w[A][3], r[A][3], f[A][3], hk[A][3], wh[A][3], r_old[A][3];
+#pragma unroll
+  for (int s = 0; s < A; ++s) {
+    rec[s] = v.particles + m.first + v.act[m.first + s];
+    const heroam_particle *p = rec[s];
+    q[s][0] = p->orientation[0]; q[s][1] = p->orientation[1];
+    q[s][2] = p->orientation[2]; q[s][3] = p->orientation[3];
+    ld3(p->position, r[s]);
+    load_w<P>(c, p->ang_velocity, w[s]);
+    load_f<P>(c, p->force, f[s]);
+  }
+  if (P::turbo) rebuild_forces<A, P>(v, r, f);
+#pragma unroll
+  for (int s = 0; s < A; ++s) half_kick<P>(c, r[s], f[s], hk[s]);
+  uint32_t steps = m.steps;
+  float time = m.time;
+  bool met = false;
+  constexpr int NP = A * (A - 1) / 2;
+  float pos_prev[LOOKAHEAD ? NP + 1 : 1];
+#pragma unroll
+  for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
+  while (steps < m.step_stop) {
+    const bool rn = renorm_at<P>(steps);
+    // first half kick + drift (simulation.c:478-490)
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      r_old[s][0] = r[s][0]; r_old[s][1] = r[s][1]; r_old[s][2] = r[s][2];
+      wh[s][0] = P::add(w[s][0], hk[s][0]);
+      wh[s][1] = P::add(w[s][1], hk[s][1]);
+      wh[s][2] = P::add(w[s][2], hk[s][2]);
+      advance_orientation<P>(c, wh[s], q[s], P::renorm_every == 1u);
+    }
+    if (P::renorm_every > 1u && rn) {  // one branch per step for all particles; uniform when the warp is in phase
+#pragma unroll
+      for (int s = 0; s < A; ++s) renormalise(q[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      pole_position<P>(c, q[s], r[s]);
+      f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
+    }
+    // all pairs in the reference's (j,k) order (:178-233)
+    // Branch-free and staged row by row: geometry and gathers of a whole row are
+    // issued before any of them is consumed.
+    float dmin = 3.0e38f;
+    uint32_t in_step = 0;
+#pragma unroll
+    for (int j = 0; j < A - 1; ++j) {
+      PairGeom g[A];
+      float tv[A];
+#pragma unroll
+      for (int k = j + 1; k < A; ++k) {
+        g[k] = pair_geom<P>(c, r[j], r[k]);
+        tv[k] = pair_gather<P>(v, g[k]);
+        if (LOOKAHEAD) {
+          // L1 prefetch by cp.async: the sector around the table position predicted for two steps
+          // from now is copied to a dummy slot of shared memory that nobody reads; the copy passes
+          // through L1, so the ordinary gather of that step finds its sector there
+          const int pi = j * A - j * (j + 1) / 2 + (k - j - 1);  // index of pair (j,k), static after unrolling
+          const float pos = P::turbo ? fmaf(g[k].d, c.inv_grid, c.pos_bias) : __fmul_rn(__fsub_rn(g[k].d, c.grid_start), c.inv_grid);
+          const float guess = fmaf(3.0f, pos, -2.0f * pos_prev[pi]);
+          pos_prev[pi] = pos;
+          const unsigned at = min((unsigned)__float2int_rz(guess), (unsigned)c.grid_len);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink_addr), "l"((P::turbo ? v.table_k : v.table) + at));
+        }
+        dmin = fminf(dmin, g[k].d);
+        if (P::count) in_step += g[k].inside ? 1u : 0u;
+      }
+#pragma unroll
+      for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
+    }
+    if (LOOKAHEAD) {
+      asm volatile("cp.async.commit_group;");
+      asm volatile("cp.async.wait_group 3;");
+    }
+    if (dmin < c.icd2) { met = true; break; }
+    // second half kick (:496-509); velocity and clock fields are written at the end
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      half_kick<P>(c, r[s], f[s], hk[s]);
+      w[s][0] = P::add(wh[s][0], hk[s][0]);
+      w[s][1] = P::add(wh[s][1], hk[s][1]);
+      w[s][2] = P::add(wh[s][2], hk[s][2]);
+    }
+    time = __fadd_rn(time, c.dt);
+    ++steps;
+    inrange_total += in_step;
+  }
+  if (LOOKAHEAD) asm volatile("cp.async.wait_all;");
+  const uint32_t done_steps = steps - m.steps;
+  if (met) {
+#pragma unroll
+    for (int s = 0; s < A; ++s) write_midstep<P>(c, rec[s], q[s], r[s], w[s], wh[s], r_old[s], time, steps > 0);
+    m.status = ST_MIDSTEP;
+  } else if (done_steps > 0) {
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      const uint32_t j = (uint32_t)(rec[s] - (v.particles + m.first));
+      write_clean<P>(c, rec[s], q[s], r[s], w[s], f[s], time, j + 1u < m.no);
+    }
+  }
+  m.steps = steps;
+  m.time = time;
+  return done_steps;
+}
+
 template <int A, class P, bool LOOKAHEAD = false>
 __global__ void __launch_bounds__(INTEGRATE_TPB)
 k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
@@ -857,113 +1038,9 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long done_steps = 0, inrange_total = 0;
   if (item < count) {
-    const Consts &c = v.c;
     const uint32_t t = list[item];
     TrajMeta m = v.meta[t];
-    heroam_particle *rec[A];
-    float q[A][4], w[A][3], r[A][3], f[A][3], hk[A][3], wh[A][3], r_old[A][3];
-#pragma unroll
-    for (int s = 0; s < A; ++s) {
-      rec[s] = v.particles + m.first + v.act[m.first + s];
-      const heroam_particle *p = rec[s];
-      q[s][0] = p->orientation[0]; q[s][1] = p->orientation[1];
-      q[s][2] = p->orientation[2]; q[s][3] = p->orientation[3];
-      ld3(p->position, r[s]);
-      load_w<P>(c, p->ang_velocity, w[s]);
-      load_f<P>(c, p->force, f[s]);
-    }
-    if (P::turbo) rebuild_forces<A, P>(v, r, f);
-#pragma unroll
-    for (int s = 0; s < A; ++s) half_kick<P>(c, r[s], f[s], hk[s]);
-    uint32_t steps = m.steps;
-    float time = m.time;
-    bool met = false;
-    constexpr int NP = A * (A - 1) / 2;
-    float pos_prev[LOOKAHEAD ? NP + 1 : 1];
-#pragma unroll
-    for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
-    while (steps < m.step_stop) {
-      const bool rn = renorm_at<P>(steps);
-      // first half kick + drift (simulation.c:478-490)
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        r_old[s][0] = r[s][0]; r_old[s][1] = r[s][1]; r_old[s][2] = r[s][2];
-        wh[s][0] = P::add(w[s][0], hk[s][0]);
-        wh[s][1] = P::add(w[s][1], hk[s][1]);
-        wh[s][2] = P::add(w[s][2], hk[s][2]);
-        advance_orientation<P>(c, wh[s], q[s], P::renorm_every == 1u);
-      }
-      if (P::renorm_every > 1u && rn) {  // one branch per step for all particles; uniform when the warp is in phase
-#pragma unroll
-        for (int s = 0; s < A; ++s) renormalise(q[s]);
-      }
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        pole_position<P>(c, q[s], r[s]);
-        f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
-      }
-      // all pairs in the reference's (j,k) order (:178-233)
-      // Branch-free and staged row by row: geometry and gathers of a whole row are
-      // issued before any of them is consumed.
-      float dmin = 3.0e38f;
-      uint32_t in_step = 0;
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) {
-        PairGeom g[A];
-        float tv[A];
-#pragma unroll
-        for (int k = j + 1; k < A; ++k) {
-          g[k] = pair_geom<P>(c, r[j], r[k]);
-          tv[k] = pair_gather<P>(v, g[k]);
-          if (LOOKAHEAD) {
-            // L1 prefetch by cp.async: the sector around the table position predicted for two steps
-            // from now is copied to a dummy slot of shared memory that nobody reads; the copy passes
-            // through L1, so the ordinary gather of that step finds its sector there
-            const int pi = j * A - j * (j + 1) / 2 + (k - j - 1);  // index of pair (j,k), static after unrolling
-            const float pos = P::turbo ? fmaf(g[k].d, c.inv_grid, c.pos_bias) : __fmul_rn(__fsub_rn(g[k].d, c.grid_start), c.inv_grid);
-            const float guess = fmaf(3.0f, pos, -2.0f * pos_prev[pi]);
-            pos_prev[pi] = pos;
-            const unsigned at = min((unsigned)__float2int_rz(guess), (unsigned)c.grid_len);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink_addr), "l"((P::turbo ? v.table_k : v.table) + at));
-          }
-          dmin = fminf(dmin, g[k].d);
-          if (P::count) in_step += g[k].inside ? 1u : 0u;
-        }
-#pragma unroll
-        for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
-      }
-      if (LOOKAHEAD) {
-        asm volatile("cp.async.commit_group;");
-        asm volatile("cp.async.wait_group 3;");
-      }
-      if (dmin < c.icd2) { met = true; break; }
-      // second half kick (:496-509); velocity and clock fields are written at the end
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        half_kick<P>(c, r[s], f[s], hk[s]);
-        w[s][0] = P::add(wh[s][0], hk[s][0]);
-        w[s][1] = P::add(wh[s][1], hk[s][1]);
-        w[s][2] = P::add(wh[s][2], hk[s][2]);
-      }
-      time = __fadd_rn(time, c.dt);
-      ++steps;
-      inrange_total += in_step;
-    }
-    if (LOOKAHEAD) asm volatile("cp.async.wait_all;");
-    done_steps = steps - m.steps;
-    if (met) {
-#pragma unroll
-      for (int s = 0; s < A; ++s) write_midstep<P>(c, rec[s], q[s], r[s], w[s], wh[s], r_old[s], time, steps > 0);
-      m.status = ST_MIDSTEP;
-    } else if (done_steps > 0) {
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        const uint32_t j = (uint32_t)(rec[s] - (v.particles + m.first));
-        write_clean<P>(c, rec[s], q[s], r[s], w[s], f[s], time, j + 1u < m.no);
-      }
-    }
-    m.steps = steps;
-    m.time = time;
+    done_steps = integrate_thread_segment<A, P, LOOKAHEAD>(v, m, sink_addr, inrange_total);
     v.meta[t] = m;
   }
   const unsigned long long ds = warp_sum_u64(done_steps);
@@ -973,6 +1050,79 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
     atomicAdd(&v.counters->pair_steps, ds * (A * (A - 1) / 2));
     atomicAdd(&v.counters->inrange_steps, ir);
   }
+}
+
+// ---------------------------------------------------------------------------------
+// k_drain<MAXW>: the latency-bound end of a run.  Once fewer trajectories are live than fill
+// the GPU and nothing is left to refill, how fast a run ends is set by the dependent steps of
+// its longest-lived trajectories (pairs that circle without meeting run to max_time: 1e7 steps
+// at the repository config), not by throughput.  Advancing every trajectory one segment per
+// pass makes each of them wait for the slowest kernel of every pass.  Here ONE THREAD owns a
+// trajectory (<= MAXW particles still moving) for a whole time slice and does, in a loop,
+// what a pass does for it: finish a pending meeting step, evaluate the exit, analyse reach
+// (whole-trajectory flight / split into core and loners / full), then fly and integrate -- with
+// the very device functions the resolve, free-flight and integrate kernels are made of, in the
+// same order, so the records it leaves are the ones those kernels leave (the results of a run
+// do not depend on how its steps are cut into segments: test_free_flight_and_splitting_change_
+// nothing).  The slice ends by the SM clock: a trajectory advances at its own chain latency for
+// the whole slice, whatever the others in the kernel are doing; between slices the host
+// re-lists the survivors by moving count, so that warps stay uniform.
+// ---------------------------------------------------------------------------------
+template <class H, int N>
+__device__ __forceinline__ void drain_fly(const DevView &v, const TrajMeta &m, uint32_t first_slot) {
+  Flyer fl[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) load_flyer<H>(v, m, first_slot + (uint32_t)i, fl[i]);
+  fly_together<H, N>(v.c, fl);
+#pragma unroll
+  for (int i = 0; i < N; ++i) land_flyer<H>(v.c, fl[i]);
+}
+
+template <int MAXW, class R, class H>
+__global__ void __launch_bounds__(DRAIN_TPB)
+k_drain(DevView v, Segments sg, uint32_t step_cap, const uint32_t *__restrict__ list, uint32_t count, long long budget_cycles) {
+  __shared__ float prefetch_sink[DRAIN_TPB];
+  const unsigned sink_addr = (unsigned)__cvta_generic_to_shared(prefetch_sink + threadIdx.x);
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  Counters work = {};
+  if (item < count) {
+    const uint32_t t = list[item];
+    TrajMeta m = v.meta[t];
+    const long long t0 = clock64();
+    for (;;) {
+      if (settle_and_exit<R, H>(v, m, step_cap, work)) break;
+      if (m.n_active + m.n_loners > (uint32_t)MAXW) break;  // cannot happen (moving counts only fall); stay safe
+      if (clock64() - t0 >= budget_cycles) break;             // clean state: any kernel can take over
+      const Schedule sc = schedule_segment(v, m, sg, step_cap, work);
+      if (sc.fly_tier < 0 && sc.bin < 0) break;  // nothing to run (never for a live trajectory)
+      if (sc.fly_tier >= 0) {
+        switch (sc.fly_count) {
+          case 1: drain_fly<H, 1>(v, m, sc.fly_first); break;
+          case 2: if (MAXW >= 2) drain_fly<H, 2>(v, m, sc.fly_first); break;
+          case 3: if (MAXW >= 3) drain_fly<H, 3>(v, m, sc.fly_first); break;
+          case 4: if (MAXW >= 4) drain_fly<H, 4>(v, m, sc.fly_first); break;
+          default: break;
+        }
+      }
+      if (sc.bin >= 0) {
+        const int width = sc.bin >= BIN_CORE ? sc.bin - BIN_CORE : sc.bin;
+        unsigned long long inrange = 0;
+        uint32_t done = 0;
+        switch (width) {
+          case 1: done = integrate_thread_segment<1, H, false>(v, m, sink_addr, inrange); break;
+          case 2: if (MAXW >= 2) done = integrate_thread_segment<2, H, true>(v, m, sink_addr, inrange); break;
+          case 3: if (MAXW >= 3) done = integrate_thread_segment<3, H, true>(v, m, sink_addr, inrange); break;
+          case 4: if (MAXW >= 4) done = integrate_thread_segment<4, H, true>(v, m, sink_addr, inrange); break;
+          default: break;
+        }
+        work.particle_steps += (unsigned long long)done * (unsigned)width;
+        work.pair_steps += (unsigned long long)done * (unsigned)(width * (width - 1) / 2);
+        work.inrange_steps += inrange;
+      }
+    }
+    v.meta[t] = m;
+  }
+  flush_work(v, work);
 }
 
 // ---------------------------------------------------------------------------------

@@ -489,21 +489,22 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
   double integrate_ms = 0.0;
   bool pending_timing = false;
   const bool trace = getenv("HEROAM_TRACE") != nullptr;  // per-pass bin populations and times on stderr
-  bool draining = false;  // set once fewer trajectories are live than fill the GPU: latency-bound regime
+  Regime rg;
   k_pool_init<<<tgrid, 128, 0, ctx->main>>>(v, pool.cap);
   CU(cudaGetLastError());
   ctx->info.kernel_launches++;
   for (;;) {
-    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BINS * sizeof(uint32_t), ctx->main));
+    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
-    Segments sg = make_segments(ctx->opt.segment_steps, draining, split_window_max(ctx));
+    Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
     sg.free_stride = ctx->free_stride;
     sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
+    sg.drain_kernel = rg.drain_kernel ? 1u : 0u;
     k_pool_resolve<R, H><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
                                                      ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
-    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
     CU(cudaStreamSynchronize(ctx->main));
     if (pending_timing) {
       float ms = 0;
@@ -519,13 +520,8 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
     uint64_t live = 0;
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
     if (live == 0) break;  // every slot is free and the index space is used up
-    {
-      uint64_t trajectories = 0;
-      for (int b = 1; b < N_BINS; ++b)
-        if (b < BIN_FREE || b >= BIN_CORE) trajectories += ctx->h_bin_count[b];
-      // fewer trajectories in the full kernels than fill the GPU once: latency-bound from here on
-      draining = trajectories < (uint64_t)ctx->sm_count * 768;
-    }
+    // a free slot claims a new trajectory in every pass while there are any: live < slots means none are left
+    update_regime(ctx, rg, ctx->h_bin_count[LIVE_SLOT] >= slots);
     ctx->info.passes++;
     if (trace) {
       fprintf(stderr, "pass %llu live %llu bins", ctx->info.passes, (unsigned long long)live);
@@ -536,7 +532,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
       const uint32_t cnt = ctx->h_bin_count[b];
       if (!cnt) continue;
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<H>(ctx, v, b, cnt, draining);
+      int rc = launch_bin<R, H>(ctx, v, b, cnt, rg.draining);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));

@@ -69,6 +69,9 @@ class Options(C.Structure):
         ("pool_slots", C.c_uint),
         ("count_work", C.c_int),
         ("no_flight", C.c_int),
+        ("no_drain_kernel", C.c_int),
+        ("drain_slice_us", C.c_uint),
+        ("drain_segment_steps", C.c_uint),
     ]
 
 
@@ -183,7 +186,8 @@ class Engine:
     """One GPU context (``heroam_gpu_create``): force table resident on the device."""
 
     def __init__(self, conf: Config, table: np.ndarray, device: int = 0, mode="exact", segment_steps: int = 0,
-                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0, no_flight: int = 0):
+                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0, no_flight: int = 0,
+                 no_drain_kernel: int = 0, drain_slice_us: int = 0, drain_segment_steps: int = 0):
         self.lib = load_library()
         self.conf = conf
         table = np.ascontiguousarray(table, dtype=np.float32)
@@ -197,6 +201,9 @@ class Engine:
         opt.pool_slots = pool_slots
         opt.count_work = count_work
         opt.no_flight = no_flight
+        opt.no_drain_kernel = no_drain_kernel
+        opt.drain_slice_us = drain_slice_us
+        opt.drain_segment_steps = drain_segment_steps
         h = C.c_void_p()
         self._check(self.lib.heroam_gpu_create(C.byref(conf), table.ctypes.data_as(C.POINTER(C.c_float)), device,
                                                C.byref(opt), C.byref(h)))

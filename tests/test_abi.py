@@ -29,12 +29,12 @@ def test_library_exports_every_declared_symbol():
     lib = engine.load_library()
     for name in declared_functions():
         assert hasattr(lib, name), f"libheroam_gpu.so does not export {name}"
-    assert lib.heroam_gpu_abi_version() == 1
+    assert lib.heroam_gpu_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
-    # heroam_options: int, uint, ull, int, int[3]; heroam_traj_result: 16 bytes
-    assert C.sizeof(engine.Options) == 32
+    # heroam_options: int, uint, ull, int, uint, int, int, int, uint, uint (+4 padding); heroam_traj_result: 16 bytes
+    assert C.sizeof(engine.Options) == 48
     assert engine.RESULT_DTYPE.itemsize == 16
     assert C.sizeof(engine.RunInfo) == 15 * 8
     assert C.sizeof(engine.Stats) == 8 * (2 + 256 + 4096 + 4096 + 8 + 1 + 1) + C.sizeof(engine.RunInfo)

@@ -52,15 +52,18 @@ def test_exact_mode_dense_droplet_golden(need_gpu, table, golden_traj):
     assert_records_equal(got, g["dense_final"], "dense droplet final state")
 
 
-@pytest.mark.parametrize("segment", [0, 257])
-def test_exact_mode_matches_oracle_at_scale(need_gpu, port, table, segment):
+@pytest.mark.parametrize("segment,no_drain", [(0, 0), (257, 0), (0, 1), (257, 1)])
+def test_exact_mode_matches_oracle_at_scale(need_gpu, port, table, segment, no_drain):
     """4096 Philox-sampled trajectories (config C2's physics; the per-trajectory
-    cross-check block), 1e5 steps, every record, outcome and work counter."""
+    cross-check block), 1e5 steps, every record, outcome and work counter -- through the
+    drain kernel (a batch this small is latency-bound from the second pass on) and with the
+    pass-per-segment schedule kept to the end."""
     n, max_time = 4096, 1.0e5
     conf = make_config(number=n, max_time=max_time)
     counts, init = port.sample(conf, HE, table, n, source="philox")
     want, wres, wctr = port.simulate(conf, HE, table, counts, init, want_counters=True)
-    with engine.Engine(conf, table, mode="exact", segment_steps=segment) as eng:
+    with engine.Engine(conf, table, mode="exact", segment_steps=segment, no_drain_kernel=no_drain,
+                       drain_segment_steps=segment) as eng:
         got, res = eng.simulate(HE, counts, init)
         info = eng.run_info()
     assert_records_equal(got, want, "final records")
@@ -183,6 +186,15 @@ def test_free_flight_and_splitting_change_nothing(need_gpu, table, mode):
     assert np.array_equal(res_a, res_b)
     assert with_flight.tobytes() == without.tobytes()
     assert info["particle_steps"] == info_b["particle_steps"] and info["pair_steps"] == info_b["pair_steps"]
+    # the drain kernel (one thread owns a trajectory for a time slice) against the pass-per-segment
+    # schedule kept to the end, and with slices and inner segments cut very differently
+    for kw in (dict(no_drain_kernel=1), dict(drain_slice_us=150, drain_segment_steps=333), dict(drain_slice_us=50000, drain_segment_steps=20000)):
+        with engine.Engine(conf, table, mode=mode, **kw) as eng:
+            other, res_c = eng.simulate(HE, counts, init)
+            info_c = eng.run_info()
+        assert np.array_equal(res_a, res_c), kw
+        assert with_flight.tobytes() == other.tobytes(), kw
+        assert info["particle_steps"] == info_c["particle_steps"] and info["pair_steps"] == info_c["pair_steps"], kw
 
 
 def test_gpu_sampler_matches_oracle_twin(need_gpu, port, table):
