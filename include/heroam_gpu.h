@@ -101,6 +101,11 @@ typedef struct heroam_options {
                              (results must not change)                                                 */
   unsigned int drain_slice_us;      /* length of a drain time slice in microseconds (0 = default)     */
   unsigned int drain_segment_steps; /* steps between re-analyses inside the drain kernel (0 = default) */
+  /* While a run is latency-bound (fewer trajectories in the integrate kernels than fill the GPU) the
+   * kernels of a pass run a time slice instead of a fixed number of steps, so that a pass lasts as long
+   * as the slice and not as long as its slowest chain of steps.                                       */
+  int no_time_slice;      /* cross-check only: 1 = fixed step segments throughout (results must not change) */
+  unsigned int pass_slice_us;       /* length of that slice in microseconds (0 = default)             */
 } heroam_options;
 
 typedef struct heroam_traj_result {

@@ -20,6 +20,9 @@ for setting in os.environ.get("SETTINGS", "off;on").split(";"):
         elif tok.startswith("us="): kw["drain_slice_us"] = int(tok[3:])
         elif tok.startswith("seg="): kw["drain_segment_steps"] = int(tok[4:])
         elif tok.startswith("base="): kw["segment_steps"] = int(tok[5:])
+        elif tok == "noslice": kw["no_time_slice"] = 1
+        elif tok.startswith("pus="): kw["pass_slice_us"] = int(tok[4:])
+        elif tok.startswith("persm="): os.environ["HEROAM_DRAIN_PER_SM"] = tok[6:]
     with engine.Engine(make_config(number=N, max_time=MT), table, mode=MODE, **kw) as eng:
         if ref is None:
             eng.run_stats(10000, min(N, 100000), first_index=10**9)  # warm-up

@@ -334,6 +334,7 @@ static DevView make_view(heroam_ctx *ctx, const Consts &c) {
   v.nbr_cap = ctx->nbr_cap;
   v.counters = ctx->d_counters;
   v.n_traj = ctx->n_traj;
+  v.slice_cycles = 0;
   return v;
 }
 
@@ -401,6 +402,32 @@ static int env_int(const char *name, int fallback) {
   return e && *e ? atoi(e) : fallback;
 }
 
+// SM clock cycles of a time slice of `us` microseconds (at the nominal clock: a slice is a
+// scheduling quantum, not a measurement)
+static long long slice_cycles_of(const heroam_ctx *ctx, unsigned us) {
+  int khz = 0;
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device) != cudaSuccess || khz <= 0) khz = 1965000;
+  return (long long)us * (long long)khz / 1000;
+}
+
+// What a pass is launched with under regime rg: segments for the resolve kernel, the time slice for
+// the integrate kernels.
+static Segments pass_segments(const heroam_ctx *ctx, const Regime &rg, DevView &v) {
+  Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
+  sg.free_stride = ctx->free_stride;
+  sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
+  sg.drain_kernel = rg.drain_kernel ? 1u : 0u;
+  v.slice_cycles = 0;
+  if (rg.draining && !ctx->opt.no_time_slice) {
+    const unsigned us = ctx->opt.pass_slice_us ? ctx->opt.pass_slice_us : 3000u;
+    v.slice_cycles = slice_cycles_of(ctx, us);
+    // a flight step is ~60 cycles of dependent instructions: flights as long as the slice
+    const long long fit = v.slice_cycles / 64;
+    if (fit > (long long)sg.flight_max) sg.flight_max = fit > 0x40000000ll ? 0x40000000u : (uint32_t)fit;
+  }
+  return sg;
+}
+
 // Decide the regime of the next pass from the populations the resolve kernel just reported.
 // can_refill: free slots would still be filled with new trajectories (streaming pool).
 static void update_regime(const heroam_ctx *ctx, Regime &rg, bool can_refill) {
@@ -408,7 +435,7 @@ static void update_regime(const heroam_ctx *ctx, Regime &rg, bool can_refill) {
   for (int b = 1; b < N_BINS; ++b)
     if (b < BIN_FREE || b >= BIN_CORE) in_kernels += ctx->h_bin_count[b];
   rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
-  static const int per_sm = env_int("HEROAM_DRAIN_PER_SM", 640);
+  const int per_sm = env_int("HEROAM_DRAIN_PER_SM", 64);  // experiments only
   // the live population only shrinks from here on, so the decision is never taken back
   if (!ctx->opt.no_drain_kernel && !ctx->opt.no_flight && !can_refill &&
       ctx->h_bin_count[LIVE_SLOT] <= (uint64_t)ctx->sm_count * per_sm)
@@ -425,9 +452,7 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, 
     // one time slice of the drain: every thread runs its trajectory until the SM clock says stop
     const unsigned slice_us = ctx->opt.drain_slice_us ? ctx->opt.drain_slice_us : 10000u;
     const unsigned seg = ctx->opt.drain_segment_steps ? ctx->opt.drain_segment_steps : 4096u;
-    int khz = 0;
-    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device));
-    const long long budget = (long long)slice_us * (long long)khz / 1000;
+    const long long budget = slice_cycles_of(ctx, slice_us);
     const Segments dsg = make_drain_segments((uint32_t)seg, split_window_max(ctx));
     const uint32_t cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)ctx->opt.max_steps;
     const unsigned dgrid = (cnt + DRAIN_TPB - 1) / DRAIN_TPB;
@@ -520,10 +545,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
-    Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
-    sg.free_stride = ctx->free_stride;
-    sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
-    sg.drain_kernel = rg.drain_kernel ? 1u : 0u;
+    const Segments sg = pass_segments(ctx, rg, v);
     k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;

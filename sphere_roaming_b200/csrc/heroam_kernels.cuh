@@ -279,6 +279,9 @@ struct Segments {
                           // the short free-flight tier would only slow per-pass progress
   uint32_t no_flight;     // 1: per-step capture -- every particle's record must be current at every step
                           // boundary, so nobody flies and nothing is split off
+  uint32_t flight_max;    // != 0 (latency-bound regimes): a whole-trajectory flight takes min(horizon, flight_max)
+                          // steps instead of its tier's fixed length -- nothing is gained from uniform trip counts
+                          // when lanes idle anyway; the tier is then only the list the flyers are put on
   uint32_t drain_kernel;  // 1: trajectories with <= DRAIN_MAX_W moving particles are only settled and listed by
                           // moving count; k_drain schedules and runs them
 };
@@ -297,15 +300,13 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
     sg.of_bin[BIN_SMEM16] = scaled(1, 8);
     sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
   } else {
-    // latency-bound regime (less than a wave of threads): every kernel lasts segment x
-    // chain latency of one step and the pass lasts as long as the slowest, so give each bin
-    // about the same wall time (~0.3 us per step at 2 particles, growing with the pair count)
-    sg.of_bin[1] = sg.of_bin[2] = sg.of_bin[3] = scaled(2, 1);
-    sg.of_bin[4] = scaled(3, 2);
-    sg.of_bin[5] = sg.of_bin[6] = base;
-    sg.of_bin[7] = sg.of_bin[8] = scaled(1, 2);
-    for (int b = THREAD_MAX_A + 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(1, 4);
-    sg.of_bin[BIN_SMEM16] = scaled(1, 8);
+    // latency-bound regime (less than a wave of threads): a kernel lasts as long as its longest
+    // chain of dependent steps, however few threads it has.  The kernels run a TIME SLICE
+    // (DevView::slice_cycles) so that every pass lasts about as long whatever the bins in it; the
+    // segments below are only upper bounds.  The warp bins keep short segments: their partner lists
+    // are built for the segment, and the reach bound grows with its length.
+    for (int b = 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(8, 1);
+    sg.of_bin[BIN_SMEM16] = scaled(8, 1);
     sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
   }
   // free flight: ~73 ns per step; the short tier is dropped while draining (schedule_segment)
@@ -314,7 +315,8 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
   // While draining a pass lasts as long as its slowest kernel, and every trajectory advances one
   // segment per pass: a long tier of 8x (65 536 steps x 73 ns = 4.8 ms for a hundred flyers) would hold
   // up the thousands of two-particle trajectories whose segment takes half of that.
-  sg.of_bin[BIN_FREE + 2] = drain ? scaled(4, 1) : scaled(8, 1);
+  sg.of_bin[BIN_FREE + 2] = scaled(8, 1);
+  sg.flight_max = drain ? scaled(8, 1) : 0u;
   // split trajectories: core and loners advance by the same fixed window.  The reach bound grows
   // with the square of the window (possible acceleration), so beyond split_window_max =
   // O(sqrt(m / f_max) / dt) everything would look linked to everything.
@@ -346,6 +348,7 @@ __host__ inline Segments make_drain_segments(uint32_t base, uint32_t split_windo
   for (int a = 0; a <= THREAD_MAX_A; ++a) sg.of_bin[BIN_CORE + a] = window;
   sg.free_stride = 0;
   sg.drain = 0;       // splitting and the short flight tier stay on
+  sg.flight_max = base * 32u;
   sg.no_flight = 0;
   sg.drain_kernel = 0;
   return sg;
@@ -357,6 +360,7 @@ __host__ inline Segments make_capture_segments(uint32_t chunk) {
   for (int b = 0; b < N_BINS; ++b) sg.of_bin[b] = chunk;
   sg.free_stride = 0;
   sg.drain = 0;
+  sg.flight_max = 0;
   sg.no_flight = 1;
   sg.drain_kernel = 0;
   return sg;
@@ -639,7 +643,8 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
   const uint32_t horizon = free_flight_horizon(v, m);
   for (int tier = 2; tier >= (sg.drain ? 1 : 0); --tier)
     if (horizon >= sg.of_bin[BIN_FREE + tier]) {
-      m.step_stop = clip(m.steps + sg.of_bin[BIN_FREE + tier]);
+      const uint32_t length = sg.flight_max ? (horizon < sg.flight_max ? horizon : sg.flight_max) : sg.of_bin[BIN_FREE + tier];
+      m.step_stop = clip(m.steps + length);
       m.status = ST_FLYING;
       out.fly_tier = tier;
       out.fly_first = 0;
@@ -921,7 +926,7 @@ __device__ __forceinline__ void rebuild_forces(const DevView &v, const float (&r
 // updates m (steps, clock, status).  Returns the number of steps completed.
 template <int A, class P, bool LOOKAHEAD>
 __device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, TrajMeta &m, const unsigned sink_addr,
-                                                             unsigned long long &inrange_total) {
+                                                             unsigned long long &inrange_total, const long long slice_cycles) {
   const Consts &c = v.c;
   heroam_particle *rec[A];
   float q[A][4], w[A][3], r[A][3], f[A][3], hk[A][3], wh[A][3], r_old[A][3];
@@ -945,7 +950,10 @@ __device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, T
   float pos_prev[LOOKAHEAD ? NP + 1 : 1];
 #pragma unroll
   for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
+  SliceClock slice;
+  slice.start(slice_cycles, steps);
   while (steps < m.step_stop) {
+    if (slice.expired(steps)) break;
     const bool rn = renorm_at<P>(steps);
     // first half kick + drift (simulation.c:478-490)
 #pragma unroll
@@ -1040,7 +1048,7 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
   if (item < count) {
     const uint32_t t = list[item];
     TrajMeta m = v.meta[t];
-    done_steps = integrate_thread_segment<A, P, LOOKAHEAD>(v, m, sink_addr, inrange_total);
+    done_steps = integrate_thread_segment<A, P, LOOKAHEAD>(v, m, sink_addr, inrange_total, v.slice_cycles);
     v.meta[t] = m;
   }
   const unsigned long long ds = warp_sum_u64(done_steps);
@@ -1109,10 +1117,10 @@ k_drain(DevView v, Segments sg, uint32_t step_cap, const uint32_t *__restrict__ 
         unsigned long long inrange = 0;
         uint32_t done = 0;
         switch (width) {
-          case 1: done = integrate_thread_segment<1, H, false>(v, m, sink_addr, inrange); break;
-          case 2: if (MAXW >= 2) done = integrate_thread_segment<2, H, true>(v, m, sink_addr, inrange); break;
-          case 3: if (MAXW >= 3) done = integrate_thread_segment<3, H, true>(v, m, sink_addr, inrange); break;
-          case 4: if (MAXW >= 4) done = integrate_thread_segment<4, H, true>(v, m, sink_addr, inrange); break;
+          case 1: done = integrate_thread_segment<1, H, false>(v, m, sink_addr, inrange, 0); break;
+          case 2: if (MAXW >= 2) done = integrate_thread_segment<2, H, true>(v, m, sink_addr, inrange, 0); break;
+          case 3: if (MAXW >= 3) done = integrate_thread_segment<3, H, true>(v, m, sink_addr, inrange, 0); break;
+          case 4: if (MAXW >= 4) done = integrate_thread_segment<4, H, true>(v, m, sink_addr, inrange, 0); break;
           default: break;
         }
         work.particle_steps += (unsigned long long)done * (unsigned)width;
@@ -1167,7 +1175,10 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_hybrid(DevView v, const 
     uint32_t steps = m.steps;
     float time = m.time;
     bool met = false;
+    SliceClock slice;
+    slice.start(v.slice_cycles, steps);
     while (steps < m.step_stop) {
+      if (slice.expired(steps)) break;
       const bool rn = renorm_at<P>(steps);
 #pragma unroll
       for (int s = 0; s < A; ++s) {
@@ -1328,7 +1339,10 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_smem(DevView v, const ui
     uint32_t steps = m.steps;
     float time = m.time;
     bool met = false;
+    SliceClock slice;
+    slice.start(v.slice_cycles, steps);
     while (steps < m.step_stop) {
+      if (slice.expired(steps)) break;
       const bool rn = renorm_at<P>(steps);
       // first half kick + drift
 #pragma unroll 2
@@ -1516,7 +1530,10 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count, b
   float time = m.time;
   bool met = false;
   unsigned long long inrange_total = 0;
+  SliceClock slice;
+  slice.start(v.slice_cycles, steps);
   while (steps < m.step_stop) {
+    if (__any_sync(0xffffffffu, slice.expired(steps))) break;  // one trajectory per warp: the lanes leave together
     const bool rn = renorm_at<P>(steps);  // one trajectory per warp: uniform
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
@@ -1591,7 +1608,10 @@ __global__ void k_integrate_records(DevView v, const uint32_t *__restrict__ list
   const uint32_t *act = v.act + m.first;
   const uint32_t a = m.n_active;
   unsigned long long done_steps = 0, inrange_total = 0;
+  SliceClock slice;
+  slice.start(v.slice_cycles, m.steps);
   while (m.steps < m.step_stop) {
+    if (slice.expired(m.steps)) break;
     for (uint32_t s = 0; s < a; ++s) {
       heroam_particle *p = base + act[s];
       float hk[3], wh[3], q[4], r[3];

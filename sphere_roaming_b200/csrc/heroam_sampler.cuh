@@ -496,10 +496,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
-    Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
-    sg.free_stride = ctx->free_stride;
-    sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
-    sg.drain_kernel = rg.drain_kernel ? 1u : 0u;
+    const Segments sg = pass_segments(ctx, rg, v);
     k_pool_resolve<R, H><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
                                                      ctx->d_free_list);
     CU(cudaGetLastError());

@@ -72,6 +72,8 @@ class Options(C.Structure):
         ("no_drain_kernel", C.c_int),
         ("drain_slice_us", C.c_uint),
         ("drain_segment_steps", C.c_uint),
+        ("no_time_slice", C.c_int),
+        ("pass_slice_us", C.c_uint),
     ]
 
 
@@ -187,7 +189,8 @@ class Engine:
 
     def __init__(self, conf: Config, table: np.ndarray, device: int = 0, mode="exact", segment_steps: int = 0,
                  max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0, no_flight: int = 0,
-                 no_drain_kernel: int = 0, drain_slice_us: int = 0, drain_segment_steps: int = 0):
+                 no_drain_kernel: int = 0, drain_slice_us: int = 0, drain_segment_steps: int = 0,
+                 no_time_slice: int = 0, pass_slice_us: int = 0):
         self.lib = load_library()
         self.conf = conf
         table = np.ascontiguousarray(table, dtype=np.float32)
@@ -204,6 +207,8 @@ class Engine:
         opt.no_drain_kernel = no_drain_kernel
         opt.drain_slice_us = drain_slice_us
         opt.drain_segment_steps = drain_segment_steps
+        opt.no_time_slice = no_time_slice
+        opt.pass_slice_us = pass_slice_us
         h = C.c_void_p()
         self._check(self.lib.heroam_gpu_create(C.byref(conf), table.ctypes.data_as(C.POINTER(C.c_float)), device,
                                                C.byref(opt), C.byref(h)))
