@@ -94,13 +94,6 @@ typedef struct heroam_options {
                              (heroam_run_info.inrange_steps) at ~3 % cost; exact mode always counts   */
   int no_flight;          /* cross-check only: 1 = no free flight and no splitting, every moving particle is
                              integrated in full every step (results must not change)                  */
-  /* The end of a run (fewer live trajectories than fill the GPU, nothing left to refill) is handed to
-   * the drain kernel: one thread owns a trajectory for a whole time slice and re-analyses, flies and
-   * integrates it on its own, instead of one segment per pass.                 */
-  int no_drain_kernel;    /* cross-check only: 1 = keep the pass-per-segment schedule to the end
-                             (results must not change)                                                 */
-  unsigned int drain_slice_us;      /* length of a drain time slice in microseconds (0 = default)     */
-  unsigned int drain_segment_steps; /* steps between re-analyses inside the drain kernel (0 = default) */
   /* While a run is latency-bound (fewer trajectories in the integrate kernels than fill the GPU) the
    * kernels of a pass run a time slice instead of a fixed number of steps, so that a pass lasts as long
    * as the slice and not as long as its slowest chain of steps.                                       */
@@ -131,6 +124,8 @@ typedef struct heroam_run_info {
   unsigned long long pair_skipped;   /* pair-steps of free-flight segments: part of pair_steps, but
                                         provably force-free and never evaluated               */
   unsigned long long free_steps;     /* particle-steps taken in free flight (part of particle_steps) */
+  double resolve_ms;      /* sum of CUDA-event times from the end of a pass's integrate kernels to the
+                             bin counts of the next being on the host (resolve kernel + copy)          */
 } heroam_run_info;
 
 #define HEROAM_HIST_N 256

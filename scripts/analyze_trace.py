@@ -7,7 +7,7 @@ bin populations at a few passes, and where the run switches to the drain regime.
 import re
 import sys
 
-PAT = re.compile(r"pass (\d+) live (\d+) bins ((?:\d+ )+) ?([\d.]+) ms  psteps (\d+) free (\d+)")
+PAT = re.compile(r"pass (\d+) live (\d+) (?:behind \d+ )?bins ((?:\d+ )+) ?([\d.]+) ms  psteps (\d+) free (\d+)")
 # bins as printed (from bin 1): 1..12 thread/hybrid kernels by moving count, 13 smem16, 14-16 warp kernels,
 # 17-19 whole-trajectory free flight (short, medium, long), 20 split-off loners, 21.. cores of split trajectories
 

@@ -15,14 +15,19 @@ table = synthetic_table()
 ref = None
 for setting in os.environ.get("SETTINGS", "off;on").split(";"):
     kw = {}
+    for k in ("HEROAM_DRAIN_PER_SM", "HEROAM_DRAIN_LIVE_PER_SM", "HEROAM_BULK_SLICE_CAP_US", "HEROAM_BULK_SEG_MULT", "HEROAM_NOSPLIT_MAX", "HEROAM_X_NOFAR", "HEROAM_X_NOEXACT", "HEROAM_BOOST_PER_SM"):
+        os.environ.pop(k, None)
     for tok in setting.split(","):
-        if tok == "off": kw["no_drain_kernel"] = 1
-        elif tok.startswith("us="): kw["drain_slice_us"] = int(tok[3:])
-        elif tok.startswith("seg="): kw["drain_segment_steps"] = int(tok[4:])
+        if tok == "on": pass
         elif tok.startswith("base="): kw["segment_steps"] = int(tok[5:])
         elif tok == "noslice": kw["no_time_slice"] = 1
         elif tok.startswith("pus="): kw["pass_slice_us"] = int(tok[4:])
-        elif tok.startswith("persm="): os.environ["HEROAM_DRAIN_PER_SM"] = tok[6:]
+        elif tok.startswith("live="): os.environ["HEROAM_DRAIN_LIVE_PER_SM"] = tok[5:]
+        elif tok.startswith("cap="): os.environ["HEROAM_BULK_SLICE_CAP_US"] = tok[4:]
+        elif tok.startswith("mult="): os.environ["HEROAM_BULK_SEG_MULT"] = tok[5:]
+        elif tok.startswith("nosplit="): os.environ["HEROAM_NOSPLIT_MAX"] = tok[8:]
+        elif tok == "nofar": os.environ["HEROAM_X_NOFAR"] = "1"
+        elif tok == "noexact": os.environ["HEROAM_X_NOEXACT"] = "1"
     with engine.Engine(make_config(number=N, max_time=MT), table, mode=MODE, **kw) as eng:
         if ref is None:
             eng.run_stats(10000, min(N, 100000), first_index=10**9)  # warm-up
@@ -33,6 +38,6 @@ for setting in os.environ.get("SETTINGS", "off;on").split(";"):
     key = (st["hist_traj_time"].tobytes(), st["hist_meet_time"].tobytes(), st["done"].tobytes(), i["particle_steps"], i["pair_steps"])
     same = "first" if ref is None else ("IDENTICAL" if key == ref else "DIFFERENT")
     if ref is None: ref = key
-    print("RESULT %-28s device_ms %9.1f wall %6.2f s  %.4g particle-steps/s  passes %5d launches %6d  done %s  %s" % (
-        setting, i["device_ms"], wall, i["particle_steps"] / i["device_ms"] * 1e3, i["passes"], i["kernel_launches"],
-        list(st["done"][:3]), same), flush=True)
+    print("RESULT %-28s device_ms %9.1f (integrate %8.1f resolve %7.1f gaps %7.1f) wall %6.2f s  %.4g particle-steps/s  passes %5d launches %6d  %s" % (
+        setting, i["device_ms"], i["integrate_ms"], i["resolve_ms"], i["device_ms"] - i["integrate_ms"] - i["resolve_ms"], wall,
+        i["particle_steps"] / i["device_ms"] * 1e3, i["passes"], i["kernel_launches"], same), flush=True)

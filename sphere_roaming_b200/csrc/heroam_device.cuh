@@ -115,6 +115,10 @@ struct DevView {       // everything a kernel needs, passed by value
   // segment says.  Used while a run is latency-bound, so that a pass lasts as long as the slice and
   // not as long as the slowest chain of steps in it (results do not depend on where segments end).
   long long slice_cycles;
+  // A time-sliced thread whose pairs are all out of reach, and provably stay so for at least this many
+  // steps, hands its trajectory back at the next check point: the re-analysis of the next pass will
+  // let it fly.  Set per pass by the host to twice the shortest flight on offer.
+  float far_exit_steps;
 };
 
 constexpr uint32_t SLICE_CHECK = 64;  // a multiple of RENORM_ALIGN: warps stay in phase

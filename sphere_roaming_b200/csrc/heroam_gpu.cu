@@ -58,7 +58,7 @@ struct heroam_ctx {
   cudaStream_t main = nullptr;
   cudaStream_t bin_stream[N_BINS] = {};
   cudaEvent_t bin_done[N_BINS] = {};
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_i0 = nullptr, ev_i1 = nullptr, ev_c0 = nullptr,
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_i0 = nullptr, ev_i1 = nullptr, ev_r = nullptr, ev_c0 = nullptr,
               ev_c1 = nullptr;
   float *d_table = nullptr;    // table_len + 1 floats: the table and a trailing 0 (the out-of-table bin)
   float *d_table_k = nullptr;  // the same multiplied by table_kappa (Turbo kernels)
@@ -69,6 +69,7 @@ struct heroam_ctx {
   size_t cap_particles = 0;
   TrajMeta *d_meta = nullptr;
   uint32_t *d_act = nullptr, *d_first = nullptr, *d_counts = nullptr, *d_bin_list = nullptr;
+  uint32_t *d_live_list = nullptr;     // 2 x cap_traj: the live trajectories listed by the last two resolve passes
   uint8_t *d_nbr_pool = nullptr;       // partner lists of the warp kernels
   uint32_t *d_nbr_start = nullptr, *d_nbr_cnt = nullptr;
   unsigned long long *d_nbr_used = nullptr;
@@ -90,6 +91,7 @@ struct heroam_ctx {
   bool uploaded = false;
   heroam_run_info info;
   int sm_count = 0;
+  int clock_khz = 0;   // nominal SM clock (queried once: the attribute call is slow)
 };
 
 extern "C" int heroam_gpu_abi_version(void) { return HEROAM_ABI_VERSION; }
@@ -181,6 +183,7 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   ctx->conf = *conf;
   ctx->opt = options;
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
   const int rc = init_context(ctx, force_list);
   if (rc) {  // whatever was created so far is released; the error message stays
     heroam_gpu_destroy(ctx);
@@ -205,6 +208,7 @@ static int init_context(heroam_ctx *ctx, const float *force_list) {
   CU(cudaEventCreate(&ctx->ev_stop));
   CU(cudaEventCreate(&ctx->ev_i0));
   CU(cudaEventCreate(&ctx->ev_i1));
+  CU(cudaEventCreate(&ctx->ev_r));
   CU(cudaEventCreate(&ctx->ev_c0));
   CU(cudaEventCreate(&ctx->ev_c1));
   CU(cudaMalloc(&ctx->d_table, ((size_t)ctx->table_len + 1) * sizeof(float)));
@@ -247,6 +251,7 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
   cudaFree(ctx->d_first);
   cudaFree(ctx->d_counts);
   cudaFree(ctx->d_bin_list);
+  cudaFree(ctx->d_live_list);
   cudaFree(ctx->d_results);
   cudaFree(ctx->d_bin_count);
   cudaFree(ctx->d_counters);
@@ -256,7 +261,7 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
     if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
     if (ctx->bin_done[b]) cudaEventDestroy(ctx->bin_done[b]);
   }
-  cudaEvent_t evs[] = {ctx->ev_start, ctx->ev_stop, ctx->ev_i0, ctx->ev_i1, ctx->ev_c0, ctx->ev_c1};
+  cudaEvent_t evs[] = {ctx->ev_start, ctx->ev_stop, ctx->ev_i0, ctx->ev_i1, ctx->ev_r, ctx->ev_c0, ctx->ev_c1};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   if (ctx->main) cudaStreamDestroy(ctx->main);
@@ -302,15 +307,17 @@ static int reserve(heroam_ctx *ctx, size_t n_traj, size_t n_particles) {
     cudaFree(ctx->d_first);
     cudaFree(ctx->d_counts);
     cudaFree(ctx->d_bin_list);
+    cudaFree(ctx->d_live_list);
     cudaFree(ctx->d_results);
     ctx->d_meta = nullptr;
-    ctx->d_first = ctx->d_counts = ctx->d_bin_list = nullptr;
+    ctx->d_first = ctx->d_counts = ctx->d_bin_list = ctx->d_live_list = nullptr;
     ctx->d_results = nullptr;
     ctx->cap_traj = 0;
     CU(cudaMalloc(&ctx->d_meta, n_traj * sizeof(TrajMeta)));
     CU(cudaMalloc(&ctx->d_first, n_traj * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_counts, n_traj * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_bin_list, (size_t)N_BINS * n_traj * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_live_list, 2 * n_traj * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_results, n_traj * sizeof(heroam_traj_result)));
     ctx->cap_traj = n_traj;
   }
@@ -335,6 +342,7 @@ static DevView make_view(heroam_ctx *ctx, const Consts &c) {
   v.counters = ctx->d_counters;
   v.n_traj = ctx->n_traj;
   v.slice_cycles = 0;
+  v.far_exit_steps = 3.0e38f;
   return v;
 }
 
@@ -394,7 +402,6 @@ static int refresh_scaled_table(heroam_ctx *ctx, const Consts &c) {
 // How a run is being scheduled at the moment.
 struct Regime {
   bool draining = false;      // fewer trajectories in the full kernels than fill the GPU: latency-bound segment table
-  bool drain_kernel = false;  // nothing left to refill and the survivors fit the GPU: k_drain owns the narrow ones
 };
 
 static int env_int(const char *name, int fallback) {
@@ -405,26 +412,28 @@ static int env_int(const char *name, int fallback) {
 // SM clock cycles of a time slice of `us` microseconds (at the nominal clock: a slice is a
 // scheduling quantum, not a measurement)
 static long long slice_cycles_of(const heroam_ctx *ctx, unsigned us) {
-  int khz = 0;
-  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device) != cudaSuccess || khz <= 0) khz = 1965000;
-  return (long long)us * (long long)khz / 1000;
+  return (long long)us * (long long)ctx->clock_khz / 1000;
 }
 
-// What a pass is launched with under regime rg: segments for the resolve kernel, the time slice for
-// the integrate kernels.
+// What a pass is launched with under regime rg: segments for the resolve kernel, the time slice and
+// the give-up distance for the integrate kernels.
 static Segments pass_segments(const heroam_ctx *ctx, const Regime &rg, DevView &v) {
-  Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
+  // Time slices only while latency-bound.  While the GPU is full, letting the unsplit narrow bins run for
+  // the length of a pass was measured to cost 30 % on a 4e6-trajectory run: a trajectory that stays in a
+  // full kernel pays full steps long after a re-analysis would have split it or let it fly.
+  const bool sliced = rg.draining && !ctx->opt.no_time_slice && !ctx->opt.no_flight;
+  Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx), sliced);
   sg.free_stride = ctx->free_stride;
   sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
-  sg.drain_kernel = rg.drain_kernel ? 1u : 0u;
   v.slice_cycles = 0;
-  if (rg.draining && !ctx->opt.no_time_slice) {
-    const unsigned us = ctx->opt.pass_slice_us ? ctx->opt.pass_slice_us : 3000u;
-    v.slice_cycles = slice_cycles_of(ctx, us);
-    // a flight step is ~60 cycles of dependent instructions: flights as long as the slice
-    const long long fit = v.slice_cycles / 64;
-    if (fit > (long long)sg.flight_max) sg.flight_max = fit > 0x40000000ll ? 0x40000000u : (uint32_t)fit;
-  }
+  v.far_exit_steps = 3.0e38f;
+  if (!sliced) return sg;
+  v.slice_cycles = slice_cycles_of(ctx, ctx->opt.pass_slice_us ? ctx->opt.pass_slice_us : 3000u);
+  // a flight step is ~60 cycles of dependent instructions: flights as long as the slice
+  const long long fit = v.slice_cycles / 64;
+  if (fit > (long long)sg.flight_max) sg.flight_max = fit > 0x40000000ll ? 0x40000000u : (uint32_t)fit;
+  // give up a slice only for a flight at least twice as long as the shortest one on offer
+  v.far_exit_steps = 2.0f * (float)sg.of_bin[BIN_FREE + 1] + 64.0f;
   return sg;
 }
 
@@ -434,12 +443,14 @@ static void update_regime(const heroam_ctx *ctx, Regime &rg, bool can_refill) {
   uint64_t in_kernels = 0;
   for (int b = 1; b < N_BINS; ++b)
     if (b < BIN_FREE || b >= BIN_CORE) in_kernels += ctx->h_bin_count[b];
-  rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
-  const int per_sm = env_int("HEROAM_DRAIN_PER_SM", 64);  // experiments only
-  // the live population only shrinks from here on, so the decision is never taken back
-  if (!ctx->opt.no_drain_kernel && !ctx->opt.no_flight && !can_refill &&
-      ctx->h_bin_count[LIVE_SLOT] <= (uint64_t)ctx->sm_count * per_sm)
-    rg.drain_kernel = true;
+  if (ctx->opt.no_time_slice) {
+    rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
+  } else {
+    // the drain policy does not split narrow trajectories, so what it would put into the full kernels
+    // is every live trajectory: switch when those fit the GPU at once
+    const int live_per_sm = env_int("HEROAM_DRAIN_LIVE_PER_SM", 400);  // experiments only
+    rg.draining = !can_refill && ctx->h_bin_count[LIVE_SLOT] <= (uint64_t)ctx->sm_count * live_per_sm;
+  }
 }
 
 // R: arithmetic of the resolve steps, P: of the integrate kernels
@@ -448,23 +459,6 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, 
   const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
-  if (bin > BIN_DRAIN) {
-    // one time slice of the drain: every thread runs its trajectory until the SM clock says stop
-    const unsigned slice_us = ctx->opt.drain_slice_us ? ctx->opt.drain_slice_us : 10000u;
-    const unsigned seg = ctx->opt.drain_segment_steps ? ctx->opt.drain_segment_steps : 4096u;
-    const long long budget = slice_cycles_of(ctx, slice_us);
-    const Segments dsg = make_drain_segments((uint32_t)seg, split_window_max(ctx));
-    const uint32_t cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)ctx->opt.max_steps;
-    const unsigned dgrid = (cnt + DRAIN_TPB - 1) / DRAIN_TPB;
-    switch (bin - BIN_DRAIN) {
-      case 1: k_drain<1, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
-      case 2: k_drain<2, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
-      case 3: k_drain<3, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
-      default: k_drain<4, R, P><<<dgrid, DRAIN_TPB, 0, s>>>(v, dsg, cap, list, cnt, budget); break;
-    }
-    CU(cudaGetLastError());
-    return HEROAM_OK;
-  }
   if (bin >= BIN_FREE && bin < BIN_CORE) {
     k_free_flight<P><<<(cnt + 127) / 128, 128, 0, s>>>(v, ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride, cnt);
     CU(cudaGetLastError());
@@ -537,6 +531,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   double integrate_ms = 0.0;
   bool pending_timing = false;
   Regime rg;
+  LiveLists lists = {nullptr, n, ctx->d_live_list};
   CU(cudaEventRecord(ctx->ev_start, ctx->main));
   CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
   k_prepare<<<tgrid, 128, 0, ctx->main>>>(v, ctx->d_first, ctx->d_counts);
@@ -546,15 +541,24 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     const Segments sg = pass_segments(ctx, rg, v);
-    k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
+    if (lists.count)
+      k_resolve_and_bin<R, H><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list,
+                                                                               ctx->d_free_list, lists);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaEventRecord(ctx->ev_r, ctx->main));
     CU(cudaStreamSynchronize(ctx->main));
+    // from the second pass on only the trajectories still live are visited
+    lists.in = lists.out;
+    lists.count = ctx->h_bin_count[LIVE_SLOT];
+    lists.out = lists.in == ctx->d_live_list ? ctx->d_live_list + ctx->cap_traj : ctx->d_live_list;
     if (pending_timing) {
       float ms = 0;
       CU(cudaEventElapsedTime(&ms, ctx->ev_i0, ctx->ev_i1));
       integrate_ms += ms;
+      CU(cudaEventElapsedTime(&ms, ctx->ev_i1, ctx->ev_r));
+      ctx->info.resolve_ms += ms;
       pending_timing = false;
     }
     uint64_t live = 0;
@@ -749,7 +753,8 @@ static int run_traced(heroam_ctx *ctx, const Consts &c, const uint32_t *counts, 
   int rc = HEROAM_OK;
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
-    k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list);
+    const LiveLists everyone = {nullptr, n, ctx->d_live_list};
+    k_resolve_and_bin<R, H><<<tgrid, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list, ctx->d_free_list, everyone);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));

@@ -34,15 +34,10 @@ constexpr int BIN_FREE = 17;      // BIN_FREE + 0: short, + 1: medium, + 2: long
 constexpr int FREE_SPLIT = 3;     // BIN_FREE + 3: loners split off a trajectory whose core keeps interacting
 constexpr int N_FREE_TIERS = 4;
 constexpr int BIN_CORE = BIN_FREE + N_FREE_TIERS;  // BIN_CORE + a: cores of split trajectories, a = 1..8 (k_integrate_thread<a>)
-// Drain regime (fewer live trajectories than fill the GPU, nothing left to refill): k_drain<w>, one thread
-// per trajectory with at most w particles still moving, which re-analyses, flies and integrates its
-// trajectory on its own for a whole time slice instead of one segment per pass.
-constexpr int BIN_DRAIN = BIN_CORE + 9;   // BIN_DRAIN + w, w = 1..DRAIN_MAX_W
-constexpr int DRAIN_MAX_W = 4;
-constexpr int N_BINS = BIN_DRAIN + DRAIN_MAX_W + 1;
+constexpr int N_BINS = BIN_CORE + 9;
 constexpr int LIVE_SLOT = N_BINS;         // bin_count[LIVE_SLOT]: live trajectories seen by the resolve kernel
-constexpr int N_BIN_COUNTERS = N_BINS + 1;
-constexpr int DRAIN_TPB = 64;
+constexpr int LAG_SLOT = N_BINS + 1;      // bin_count[LAG_SLOT]: 0xffffffff - (fewest steps done by a live trajectory)
+constexpr int N_BIN_COUNTERS = N_BINS + 2;
 constexpr int FREE_MAX_A = 8;     // the free-flight analysis is done for trajectories with <= 8 moving particles
 constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
 constexpr int INTEGRATE_TPB = 128;
@@ -279,14 +274,16 @@ struct Segments {
                           // the short free-flight tier would only slow per-pass progress
   uint32_t no_flight;     // 1: per-step capture -- every particle's record must be current at every step
                           // boundary, so nobody flies and nothing is split off
-  uint32_t flight_max;    // != 0 (latency-bound regimes): a whole-trajectory flight takes min(horizon, flight_max)
-                          // steps instead of its tier's fixed length -- nothing is gained from uniform trip counts
-                          // when lanes idle anyway; the tier is then only the list the flyers are put on
-  uint32_t drain_kernel;  // 1: trajectories with <= DRAIN_MAX_W moving particles are only settled and listed by
-                          // moving count; k_drain schedules and runs them
+  uint32_t flight_max;    // != 0: a whole-trajectory flight of the medium or long tier takes min(horizon, flight_max)
+                          // steps instead of the tier's fixed length (the tier is then only the list the flyers
+                          // are put on): the long flights are few, and they are the pairs whose chains end a run
+  uint32_t nosplit_max;   // trajectories with at most this many moving particles are not split into core and loners
+                          // (a core advances one bounded window per pass; unsplit it runs a whole time slice)
 };
 
-__host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split_window_max) {
+// sliced: the integrate kernels of the pass run a time slice (DevView::slice_cycles), so the segments
+// of the narrow bins are only upper bounds; otherwise (cross-check) fixed step segments throughout.
+__host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split_window_max, bool sliced) {
   Segments sg;
   auto scaled = [base](uint32_t num, uint32_t den) { uint32_t v = (uint32_t)((unsigned long long)base * num / den); return v ? v : 1u; };
   sg.of_bin[0] = base;
@@ -300,14 +297,24 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
     sg.of_bin[BIN_SMEM16] = scaled(1, 8);
     sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
   } else {
-    // latency-bound regime (less than a wave of threads): a kernel lasts as long as its longest
-    // chain of dependent steps, however few threads it has.  The kernels run a TIME SLICE
-    // (DevView::slice_cycles) so that every pass lasts about as long whatever the bins in it; the
-    // segments below are only upper bounds.  The warp bins keep short segments: their partner lists
-    // are built for the segment, and the reach bound grows with its length.
-    for (int b = 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(8, 1);
-    sg.of_bin[BIN_SMEM16] = scaled(8, 1);
+    // latency-bound regime (less than a wave of threads): every kernel lasts segment x
+    // chain latency of one step and the pass lasts as long as the slowest, so give each bin
+    // about the same wall time (~0.3 us per step at 2 particles, growing with the pair count)
+    sg.of_bin[1] = sg.of_bin[2] = sg.of_bin[3] = scaled(2, 1);
+    sg.of_bin[4] = scaled(3, 2);
+    sg.of_bin[5] = sg.of_bin[6] = base;
+    sg.of_bin[7] = sg.of_bin[8] = scaled(1, 2);
+    for (int b = THREAD_MAX_A + 1; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = scaled(1, 4);
+    sg.of_bin[BIN_SMEM16] = scaled(1, 8);
     sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
+  }
+  if (sliced) {
+    // The integrate kernels run a time slice (DevView::slice_cycles): a pass then lasts as long as
+    // the slice whatever the bins in it, every trajectory advancing at its own chain latency, and
+    // the segments are only upper bounds.  The warp bins keep theirs: their partner lists are built
+    // for the segment, and the reach bound grows with its length.
+    for (int b = 2; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = 1u << 20;
+    sg.of_bin[BIN_SMEM16] = 1u << 20;
   }
   // free flight: ~73 ns per step; the short tier is dropped while draining (schedule_segment)
   sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
@@ -315,8 +322,8 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
   // While draining a pass lasts as long as its slowest kernel, and every trajectory advances one
   // segment per pass: a long tier of 8x (65 536 steps x 73 ns = 4.8 ms for a hundred flyers) would hold
   // up the thousands of two-particle trajectories whose segment takes half of that.
-  sg.of_bin[BIN_FREE + 2] = scaled(8, 1);
-  sg.flight_max = drain ? scaled(8, 1) : 0u;
+  sg.of_bin[BIN_FREE + 2] = (drain && !sliced) ? scaled(4, 1) : scaled(8, 1);
+  sg.flight_max = sliced ? scaled(8, 1) : 0u;
   // split trajectories: core and loners advance by the same fixed window.  The reach bound grows
   // with the square of the window (possible acceleration), so beyond split_window_max =
   // O(sqrt(m / f_max) / dt) everything would look linked to everything.
@@ -326,31 +333,8 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
   for (int a = 0; a <= THREAD_MAX_A; ++a) sg.of_bin[BIN_CORE + a] = window;
   sg.free_stride = 0;
   sg.drain = drain ? 1u : 0u;
+  sg.nosplit_max = drain ? (uint32_t)THREAD_MAX_A : 0u;
   sg.no_flight = 0;
-  sg.drain_kernel = 0;
-  return sg;
-}
-
-// Segments the threads of k_drain schedule themselves with.  Nothing waits for anything here, so
-// lengths are chosen for the trajectory alone: re-analysis is cheap (a few hundred instructions
-// against ~100 per particle-step), so interacting segments are short -- the sooner a pair that has
-// flown apart is found out, the sooner it flies (a flight step has a quarter of the dependency
-// chain of a full step) -- and flights take the longest tier their horizon covers.
-__host__ inline Segments make_drain_segments(uint32_t base, uint32_t split_window_max) {
-  Segments sg;
-  for (int b = 0; b < N_BINS; ++b) sg.of_bin[b] = base;
-  sg.of_bin[BIN_FREE + 0] = base / 8u ? base / 8u : 1u;
-  sg.of_bin[BIN_FREE + 1] = base;
-  sg.of_bin[BIN_FREE + 2] = base * 8u;
-  uint32_t window = base;
-  while (window > split_window_max && window > 64u) window /= 2u;
-  sg.of_bin[BIN_FREE + FREE_SPLIT] = window;
-  for (int a = 0; a <= THREAD_MAX_A; ++a) sg.of_bin[BIN_CORE + a] = window;
-  sg.free_stride = 0;
-  sg.drain = 0;       // splitting and the short flight tier stay on
-  sg.flight_max = base * 32u;
-  sg.no_flight = 0;
-  sg.drain_kernel = 0;
   return sg;
 }
 
@@ -361,8 +345,8 @@ __host__ inline Segments make_capture_segments(uint32_t chunk) {
   sg.free_stride = 0;
   sg.drain = 0;
   sg.flight_max = 0;
+  sg.nosplit_max = 0;
   sg.no_flight = 1;
-  sg.drain_kernel = 0;
   return sg;
 }
 
@@ -643,7 +627,8 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
   const uint32_t horizon = free_flight_horizon(v, m);
   for (int tier = 2; tier >= (sg.drain ? 1 : 0); --tier)
     if (horizon >= sg.of_bin[BIN_FREE + tier]) {
-      const uint32_t length = sg.flight_max ? (horizon < sg.flight_max ? horizon : sg.flight_max) : sg.of_bin[BIN_FREE + tier];
+      const uint32_t length = (sg.flight_max && tier >= 1) ? (horizon < sg.flight_max ? horizon : sg.flight_max)
+                                                           : sg.of_bin[BIN_FREE + tier];
       m.step_stop = clip(m.steps + length);
       m.status = ST_FLYING;
       out.fly_tier = tier;
@@ -655,7 +640,7 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
   // While draining, a narrow trajectory advances further per pass in the kernel of its size
   // (longer segments) than split with the bounded window; wide ones always gain from splitting.
   const uint32_t window = sg.of_bin[BIN_FREE + FREE_SPLIT];
-  if (a >= 2 && a <= (uint32_t)MAX_ACTIVE && window >= 64u && (!sg.drain || a > (uint32_t)THREAD_MAX_A)) {
+  if (a >= 2 && a <= (uint32_t)MAX_ACTIVE && window >= 64u && a > sg.nosplit_max) {
     Reach rc;
     rc.init(v, m, a, window);
     rc.solve();
@@ -703,12 +688,21 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
 // slot in its act list).
 __device__ inline void append_schedule(const Schedule &sc, uint32_t t, uint32_t stride, uint32_t *__restrict__ bin_count,
                                        uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list,
-                                       uint32_t free_stride) {
+                                       uint32_t free_stride, uint32_t *__restrict__ live_out, uint32_t steps_done) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned peers = __match_any_sync(0xffffffffu, sc.bin);
-  {  // live trajectories (anything scheduled), one atomic per warp
-    const unsigned alive = __ballot_sync(0xffffffffu, sc.bin >= 0 || sc.fly_tier >= 0);
-    if (lane == 0 && alive) atomicAdd(bin_count + LIVE_SLOT, (uint32_t)__popc(alive));
+  {  // live trajectories (anything scheduled): counted and listed for the next pass, one atomic per warp
+    const bool is_live = sc.bin >= 0 || sc.fly_tier >= 0;
+    const unsigned alive = __ballot_sync(0xffffffffu, is_live);
+    if (alive) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(bin_count + LIVE_SLOT, (uint32_t)__popc(alive));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_live) live_out[base + __popc(alive & ((1u << lane) - 1u))] = t;
+      // the trajectory furthest behind: the longest chain of steps still to come bounds the end of the run
+      const uint32_t lag = __reduce_max_sync(0xffffffffu, is_live ? 0xffffffffu - steps_done : 0u);
+      if (lane == 0) atomicMax(bin_count + LAG_SLOT, lag);
+    }
   }
   if (sc.bin >= 0) {
     const int leader = __ffs(peers) - 1;
@@ -762,32 +756,38 @@ template <class P, class H>
 __device__ inline Schedule resolve_live(const DevView &v, TrajMeta &m, const Segments &sg, uint32_t step_cap,
                                         Counters &work) {
   if (settle_and_exit<P, H>(v, m, step_cap, work)) return Schedule();
-  const uint32_t moving = m.n_active + m.n_loners;
-  if (sg.drain_kernel && !sg.no_flight && moving >= 1u && moving <= (uint32_t)DRAIN_MAX_W) {
-    Schedule out;  // k_drain does its own scheduling: only list the trajectory by its moving count
-    out.bin = BIN_DRAIN + (int)moving;
-    return out;
-  }
   return schedule_segment(v, m, sg, step_cap, work);
 }
 
 // ---------------------------------------------------------------------------------
 // k_resolve_and_bin: one thread per trajectory, once per pass (fixed batch).
 // ---------------------------------------------------------------------------------
+// The trajectories to visit: all of them (live_in == nullptr, the first pass) or the ones the
+// previous pass listed as still live -- late in a run they are a small fraction of the batch.
+struct LiveLists {
+  const uint32_t *in;   // nullptr: visit trajectory t = thread index, t < count
+  uint32_t count;
+  uint32_t *out;        // the trajectories still live after this pass, in no particular order
+};
+
 template <class P, class H>
 __global__ void k_resolve_and_bin(DevView v, Segments sg, uint32_t step_cap, uint32_t *__restrict__ bin_count,
-                                  uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+                                  uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list, LiveLists live) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t t = idx;
   Counters work = {};
   Schedule sc;
-  if (t < v.n_traj) {
+  uint32_t steps_done = 0;
+  if (idx < live.count) {
+    if (live.in) t = live.in[idx];
     TrajMeta m = v.meta[t];
     if (m.status < ST_DONE) {
       sc = resolve_live<P, H>(v, m, sg, step_cap, work);
       v.meta[t] = m;
+      steps_done = m.steps;
     }
   }
-  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
+  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride, live.out, steps_done);
   flush_work(v, work);
 }
 
@@ -921,6 +921,30 @@ __device__ __forceinline__ void rebuild_forces(const DevView &v, const float (&r
 // (all of it drain) takes 4.2 s with it, 4.65 s without, 5.1 s with the one-step look-ahead
 // into registers it replaced (DESIGN.md section 7 has the other variants).
 // ---------------------------------------------------------------------------------
+// free_flight_horizon on the state a kernel holds in registers (same bound, same constants): the number
+// of steps for which no pair can come within reach; only meaningful when every pair is out of reach now.
+template <int A, class P>
+__device__ __forceinline__ float flight_horizon_now(const Consts &c, const float (&r)[A][3], const float (&w)[A][3]) {
+  float reach[A];
+#pragma unroll
+  for (int s = 0; s < A; ++s) {
+    float wr[3];
+    unscale_w<P>(c, w[s], wr);
+    reach[s] = sqrtf(wr[0] * wr[0] + wr[1] * wr[1] + wr[2] * wr[2]) * c.radius * c.dt * 1.01f + 2.0e-6f * c.radius;
+  }
+  const float d_far = sqrtf(c.far2) * 1.00001f + 1.0e-3f;
+  float horizon = 4.0e9f;
+#pragma unroll
+  for (int j = 0; j < A - 1; ++j)
+#pragma unroll
+    for (int k = j + 1; k < A; ++k) {
+      const float dx = r[j][0] - r[k][0], dy = r[j][1] - r[k][1], dz = r[j][2] - r[k][2];
+      const float gap = sqrtf(dx * dx + dy * dy + dz * dz) - d_far;
+      horizon = fminf(horizon, gap / (reach[j] + reach[k]) * 0.999f - 2.0f);
+    }
+  return horizon;
+}
+
 // One segment of a trajectory with A moving particles, by one thread: loads the records, runs
 // steps [m.steps, m.step_stop) or up to a meeting, leaves the records (clean, or mid-step) and
 // updates m (steps, clock, status).  Returns the number of steps completed.
@@ -952,8 +976,14 @@ __device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, T
   for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
   SliceClock slice;
   slice.start(slice_cycles, steps);
+  float dmin_last = 0.0f;
   while (steps < m.step_stop) {
-    if (slice.expired(steps)) break;
+    // end of the time slice -- or, at the same check points, every pair far out of reach: hand the
+    // trajectory back for re-analysis (it will fly) instead of spending full steps on it
+    if (steps == slice.next_check) {
+      if (A >= 2 && dmin_last > c.far2 && flight_horizon_now<A, P>(c, r, w) >= v.far_exit_steps) break;
+      if (slice.expired(steps)) break;
+    }
     const bool rn = renorm_at<P>(steps);
     // first half kick + drift (simulation.c:478-490)
 #pragma unroll
@@ -1008,6 +1038,7 @@ __device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, T
       asm volatile("cp.async.wait_group 3;");
     }
     if (dmin < c.icd2) { met = true; break; }
+    dmin_last = dmin;
     // second half kick (:496-509); velocity and clock fields are written at the end
 #pragma unroll
     for (int s = 0; s < A; ++s) {
@@ -1058,79 +1089,6 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
     atomicAdd(&v.counters->pair_steps, ds * (A * (A - 1) / 2));
     atomicAdd(&v.counters->inrange_steps, ir);
   }
-}
-
-// ---------------------------------------------------------------------------------
-// k_drain<MAXW>: the latency-bound end of a run.  Once fewer trajectories are live than fill
-// the GPU and nothing is left to refill, how fast a run ends is set by the dependent steps of
-// its longest-lived trajectories (pairs that circle without meeting run to max_time: 1e7 steps
-// at the repository config), not by throughput.  Advancing every trajectory one segment per
-// pass makes each of them wait for the slowest kernel of every pass.  Here ONE THREAD owns a
-// trajectory (<= MAXW particles still moving) for a whole time slice and does, in a loop,
-// what a pass does for it: finish a pending meeting step, evaluate the exit, analyse reach
-// (whole-trajectory flight / split into core and loners / full), then fly and integrate -- with
-// the very device functions the resolve, free-flight and integrate kernels are made of, in the
-// same order, so the records it leaves are the ones those kernels leave (the results of a run
-// do not depend on how its steps are cut into segments: test_free_flight_and_splitting_change_
-// nothing).  The slice ends by the SM clock: a trajectory advances at its own chain latency for
-// the whole slice, whatever the others in the kernel are doing; between slices the host
-// re-lists the survivors by moving count, so that warps stay uniform.
-// ---------------------------------------------------------------------------------
-template <class H, int N>
-__device__ __forceinline__ void drain_fly(const DevView &v, const TrajMeta &m, uint32_t first_slot) {
-  Flyer fl[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) load_flyer<H>(v, m, first_slot + (uint32_t)i, fl[i]);
-  fly_together<H, N>(v.c, fl);
-#pragma unroll
-  for (int i = 0; i < N; ++i) land_flyer<H>(v.c, fl[i]);
-}
-
-template <int MAXW, class R, class H>
-__global__ void __launch_bounds__(DRAIN_TPB)
-k_drain(DevView v, Segments sg, uint32_t step_cap, const uint32_t *__restrict__ list, uint32_t count, long long budget_cycles) {
-  __shared__ float prefetch_sink[DRAIN_TPB];
-  const unsigned sink_addr = (unsigned)__cvta_generic_to_shared(prefetch_sink + threadIdx.x);
-  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-  Counters work = {};
-  if (item < count) {
-    const uint32_t t = list[item];
-    TrajMeta m = v.meta[t];
-    const long long t0 = clock64();
-    for (;;) {
-      if (settle_and_exit<R, H>(v, m, step_cap, work)) break;
-      if (m.n_active + m.n_loners > (uint32_t)MAXW) break;  // cannot happen (moving counts only fall); stay safe
-      if (clock64() - t0 >= budget_cycles) break;             // clean state: any kernel can take over
-      const Schedule sc = schedule_segment(v, m, sg, step_cap, work);
-      if (sc.fly_tier < 0 && sc.bin < 0) break;  // nothing to run (never for a live trajectory)
-      if (sc.fly_tier >= 0) {
-        switch (sc.fly_count) {
-          case 1: drain_fly<H, 1>(v, m, sc.fly_first); break;
-          case 2: if (MAXW >= 2) drain_fly<H, 2>(v, m, sc.fly_first); break;
-          case 3: if (MAXW >= 3) drain_fly<H, 3>(v, m, sc.fly_first); break;
-          case 4: if (MAXW >= 4) drain_fly<H, 4>(v, m, sc.fly_first); break;
-          default: break;
-        }
-      }
-      if (sc.bin >= 0) {
-        const int width = sc.bin >= BIN_CORE ? sc.bin - BIN_CORE : sc.bin;
-        unsigned long long inrange = 0;
-        uint32_t done = 0;
-        switch (width) {
-          case 1: done = integrate_thread_segment<1, H, false>(v, m, sink_addr, inrange, 0); break;
-          case 2: if (MAXW >= 2) done = integrate_thread_segment<2, H, true>(v, m, sink_addr, inrange, 0); break;
-          case 3: if (MAXW >= 3) done = integrate_thread_segment<3, H, true>(v, m, sink_addr, inrange, 0); break;
-          case 4: if (MAXW >= 4) done = integrate_thread_segment<4, H, true>(v, m, sink_addr, inrange, 0); break;
-          default: break;
-        }
-        work.particle_steps += (unsigned long long)done * (unsigned)width;
-        work.pair_steps += (unsigned long long)done * (unsigned)(width * (width - 1) / 2);
-        work.inrange_steps += inrange;
-      }
-    }
-    v.meta[t] = m;
-  }
-  flush_work(v, work);
 }
 
 // ---------------------------------------------------------------------------------

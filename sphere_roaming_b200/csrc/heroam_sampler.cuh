@@ -293,6 +293,7 @@ struct PoolParams {
   uint32_t cap;                 // records per slot
   uint32_t n_points;
   DevStats *stats;              // n_points blocks
+  uint32_t refill;              // 0: the index space is used up (the host has seen free slots stay free)
   unsigned long long point_end[MAX_SWEEP_POINTS];    // exclusive end of each point in the index space
   unsigned long long point_first[MAX_SWEEP_POINTS];  // its first Philox trajectory index
   double point_limit[MAX_SWEEP_POINTS];              // its exp(-lambda)
@@ -313,11 +314,14 @@ __global__ void k_pool_init(DevView v, uint32_t cap) {
 template <class P, class H>
 __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t step_cap,
                                uint32_t *__restrict__ bin_count, uint32_t *__restrict__ bin_list,
-                               uint2 *__restrict__ free_list) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+                               uint2 *__restrict__ free_list, LiveLists live) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t t = idx;
   Counters work = {};
   Schedule sc;
-  if (t < v.n_traj) {
+  uint32_t steps_done = 0;
+  if (idx < live.count) {
+    if (live.in) t = live.in[idx];
     TrajMeta m = v.meta[t];
     // a freshly spawned trajectory can be over at once (nobody moving), hence the loop
     for (;;) {
@@ -333,6 +337,7 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
       // (millions, late in a run) would otherwise all serialise on the cursor's atomic in every pass,
       // ~1 ns each -- 4 ms per pass with 4e6 free slots.  The cursor only grows, so a stale value
       // can only send a thread on to the atomic, never past a trajectory.
+      if (!pool.refill) break;
       if (*reinterpret_cast<volatile unsigned long long *>(pool.cursor) >= pool.count) break;
       const unsigned long long idx = atomicAdd(pool.cursor, 1ull);
       if (idx >= pool.count) break;
@@ -359,8 +364,9 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
       m.status = ST_LIVE;
     }
     v.meta[t] = m;
+    steps_done = m.steps;
   }
-  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride);
+  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride, live.out, steps_done);
   flush_work(v, work);
 }
 
@@ -477,7 +483,10 @@ static uint32_t pool_slot_capacity(double lambda) {
 }
 
 template <class R, class H>
-static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, uint32_t slots) {
+static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in, uint32_t slots) {
+  PoolParams pool = pool_in;
+  pool.refill = 1;
+  LiveLists lists = {nullptr, slots, ctx->d_live_list};
   DevView v = make_view(ctx, c);
   if (H::turbo) {
     int rc = refresh_scaled_table(ctx, c);
@@ -497,31 +506,44 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, ui
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     const Segments sg = pass_segments(ctx, rg, v);
-    k_pool_resolve<R, H><<<tgrid, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count, ctx->d_bin_list,
-                                                     ctx->d_free_list);
+    if (lists.count)
+      k_pool_resolve<R, H><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count,
+                                                                           ctx->d_bin_list, ctx->d_free_list, lists);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
     CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaEventRecord(ctx->ev_r, ctx->main));
     CU(cudaStreamSynchronize(ctx->main));
     if (pending_timing) {
       float ms = 0;
       CU(cudaEventElapsedTime(&ms, ctx->ev_i0, ctx->ev_i1));
       integrate_ms += ms;
+      const float pass_ms = ms;
+      CU(cudaEventElapsedTime(&ms, ctx->ev_i1, ctx->ev_r));
+      ctx->info.resolve_ms += ms;
       pending_timing = false;
       if (trace) {
         Counters now;
         cudaMemcpy(&now, ctx->d_counters, sizeof now, cudaMemcpyDeviceToHost);
-        fprintf(stderr, " %.3f ms  psteps %llu free %llu\n", ms, now.particle_steps, now.free_steps);
+        fprintf(stderr, " %.3f ms  psteps %llu free %llu resolve %.3f ms\n", (double)pass_ms, now.particle_steps, now.free_steps, ms);
       }
     }
     uint64_t live = 0;
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
     if (live == 0) break;  // every slot is free and the index space is used up
-    // a free slot claims a new trajectory in every pass while there are any: live < slots means none are left
-    update_regime(ctx, rg, ctx->h_bin_count[LIVE_SLOT] >= slots);
+    // a free slot claims a new trajectory in every pass while there are any: live < slots means none are left,
+    // and from then on only the slots listed as live need a visit
+    if (ctx->h_bin_count[LIVE_SLOT] < slots) pool.refill = 0;
+    update_regime(ctx, rg, pool.refill != 0);
+    if (!pool.refill) {
+      lists.in = lists.out;
+      lists.count = ctx->h_bin_count[LIVE_SLOT];
+      lists.out = lists.in == ctx->d_live_list ? ctx->d_live_list + ctx->cap_traj : ctx->d_live_list;
+    }
     ctx->info.passes++;
     if (trace) {
-      fprintf(stderr, "pass %llu live %llu bins", ctx->info.passes, (unsigned long long)live);
+      fprintf(stderr, "pass %llu live %llu behind %u bins", ctx->info.passes, (unsigned long long)live,
+              0xffffffffu - ctx->h_bin_count[LAG_SLOT]);
       for (int b = 1; b < N_BINS; ++b) fprintf(stderr, " %u", ctx->h_bin_count[b]);
     }
     CU(cudaEventRecord(ctx->ev_i0, ctx->main));

@@ -69,9 +69,6 @@ class Options(C.Structure):
         ("pool_slots", C.c_uint),
         ("count_work", C.c_int),
         ("no_flight", C.c_int),
-        ("no_drain_kernel", C.c_int),
-        ("drain_slice_us", C.c_uint),
-        ("drain_segment_steps", C.c_uint),
         ("no_time_slice", C.c_int),
         ("pass_slice_us", C.c_uint),
     ]
@@ -94,6 +91,7 @@ class RunInfo(C.Structure):
         ("d2h_bytes", C.c_ulonglong),
         ("pair_skipped", C.c_ulonglong),
         ("free_steps", C.c_ulonglong),
+        ("resolve_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -189,7 +187,6 @@ class Engine:
 
     def __init__(self, conf: Config, table: np.ndarray, device: int = 0, mode="exact", segment_steps: int = 0,
                  max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0, no_flight: int = 0,
-                 no_drain_kernel: int = 0, drain_slice_us: int = 0, drain_segment_steps: int = 0,
                  no_time_slice: int = 0, pass_slice_us: int = 0):
         self.lib = load_library()
         self.conf = conf
@@ -204,9 +201,6 @@ class Engine:
         opt.pool_slots = pool_slots
         opt.count_work = count_work
         opt.no_flight = no_flight
-        opt.no_drain_kernel = no_drain_kernel
-        opt.drain_slice_us = drain_slice_us
-        opt.drain_segment_steps = drain_segment_steps
         opt.no_time_slice = no_time_slice
         opt.pass_slice_us = pass_slice_us
         h = C.c_void_p()
