@@ -70,6 +70,10 @@ class RefOracle:
         L.ref_initialize.argtypes = [C.c_ulonglong, C.POINTER(Config), _fp, _u32p, C.c_void_p, C.c_long]
         L.ref_simulate.restype = None
         L.ref_simulate.argtypes = [C.c_ulonglong, C.POINTER(Config), _fp, C.c_int, _u32p, C.c_void_p, C.c_int, C.c_int]
+        if hasattr(L, "ref_simulate_guarded"):
+            L.ref_simulate_guarded.restype = None
+            L.ref_simulate_guarded.argtypes = [C.c_ulonglong, C.POINTER(Config), _fp, C.c_int, _u32p, C.c_void_p, C.c_int,
+                                               C.c_int, C.c_void_p]
         L.ref_calculate_force.restype = None
         L.ref_calculate_force.argtypes = [C.c_uint, C.c_void_p, C.POINTER(Config), _fp]
         if hasattr(L, "ref_simulate_traced"):
@@ -152,6 +156,18 @@ class RefOracle:
         self.lib.ref_simulate(he_number, C.byref(conf), _ptr(table, _fp), len(counts), _ptr(counts, _u32p),
                               out.ctypes.data, nthreads, 1 if dynamic else 0)
         return out
+
+    def simulate_guarded(self, conf: Config, he_number: int, table: np.ndarray, counts: np.ndarray, flat: np.ndarray,
+                         nthreads: int = 0, dynamic: bool = True):
+        """simulate_particles over a batch with the harness's guard against the reference's one
+        non-terminating case (every particle frozen, `==` criterion unmet: SURVEY.md Q4).  Returns
+        (advanced copy, deadlocked[u1] per trajectory)."""
+        out = np.ascontiguousarray(flat.copy())
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        dead = np.zeros(len(counts), dtype=np.uint8)
+        self.lib.ref_simulate_guarded(he_number, C.byref(conf), _ptr(table, _fp), len(counts), _ptr(counts, _u32p),
+                                      out.ctypes.data, nthreads, 1 if dynamic else 0, dead.ctypes.data)
+        return out, dead
 
     def simulate_traced(self, conf: Config, he_number: int, table: np.ndarray, particles: np.ndarray, cap_steps: int):
         """One trajectory with saveflag=1: (snapshots[steps, no], final records).  The snapshots are

@@ -23,6 +23,7 @@
  *   (simulation.c:310-331, first use is `+=` at :507).  ref_initialize zeroes
  *   it so that results are defined.
  */
+#include <setjmp.h>
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,11 +40,24 @@
  * /Step_<step>/particles. */
 static _Thread_local Particle *g_trace_out = NULL;
 static _Thread_local unsigned long g_trace_cap = 0, g_trace_steps = 0;
+/* Guard against the reference's one non-terminating case: once every particle is frozen
+ * but find_success's `==` criterion is unmet, no clock advances any more and `while (!sucess && time <
+ * max_time)` (simulation.c:469) spins forever.  ref_simulate_guarded runs the reference with saveflag = 1,
+ * so that it calls save_timestep_to_hdf5 (below) at the top of every iteration; there the state is
+ * inspected, and on that condition the harness steps out of simulate_particles with longjmp.  The
+ * records are then exactly what every further iteration would leave them as. */
+static _Thread_local int g_guard = 0;
+static _Thread_local jmp_buf g_guard_jmp;
 hid_t initialize_file(const char *filename) { (void)filename; return 0; }
 hid_t open_file(const char *filename) { (void)filename; return 0; }
 herr_t save_timestep_to_hdf5(const hid_t file_id, const unsigned int step,
                              const Particles *particles) {
   (void)file_id;
+  if (g_guard && step > 0) {
+    unsigned int i = 0;
+    while (i < particles->no && particles->particle[i].success) ++i;
+    if (i == particles->no && !find_success(particles)) longjmp(g_guard_jmp, 1);
+  }
   if (g_trace_out) {
     if (step != g_trace_steps) return -1; /* the reference numbers the groups 0, 1, 2, ... */
     if (g_trace_steps < g_trace_cap)
@@ -174,6 +188,49 @@ void ref_simulate(unsigned long long he_number, const struct config *conf,
 #pragma omp parallel for
     for (int i = 0; i < number; ++i)
       simulate_particles(conf, he_number, force_list, all + i);
+  }
+  free(all);
+}
+
+/* The same loop with the guard armed (see g_guard): deadlocked[i] = 1 for the trajectories the
+ * reference itself would never return from.  The only difference from ref_simulate is saveflag = 1
+ * (one call of the no-op save_timestep_to_hdf5 per iteration). */
+void ref_simulate_guarded(unsigned long long he_number, const struct config *conf,
+                          const float *force_list, int number,
+                          const unsigned int *counts, Particle *flat, int nthreads,
+                          int schedule_dynamic, unsigned char *deadlocked) {
+  Particles *all = (Particles *)malloc((size_t)number * sizeof(Particles));
+  long at = 0;
+  for (int i = 0; i < number; ++i) {
+    all[i].no = counts[i];
+    all[i].index = (unsigned int)i;
+    all[i].particle = flat + at;
+    at += counts[i];
+    deadlocked[i] = 0;
+  }
+  struct config c = *conf;
+  c.saveflag = 1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+  if (schedule_dynamic) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < number; ++i) {
+      g_guard = 1;
+      if (setjmp(g_guard_jmp) == 0) simulate_particles(&c, he_number, force_list, all + i);
+      else deadlocked[i] = 1;
+      g_guard = 0;
+    }
+  } else {
+#pragma omp parallel for
+    for (int i = 0; i < number; ++i) {
+      g_guard = 1;
+      if (setjmp(g_guard_jmp) == 0) simulate_particles(&c, he_number, force_list, all + i);
+      else deadlocked[i] = 1;
+      g_guard = 0;
+    }
   }
   free(all);
 }

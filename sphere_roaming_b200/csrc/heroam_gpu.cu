@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "heroam_kernels.cuh"
@@ -84,6 +85,10 @@ struct heroam_ctx {
   Counters *d_counters = nullptr;
   uint32_t *h_bin_count = nullptr;  // pinned
   Counters *h_counters = nullptr;   // pinned
+  // page-locked staging of heroam_gpu_simulate_batch (the reference's pointer-per-trajectory layout is
+  // gathered into it, uploaded in one copy, and scattered back from it), grown on demand
+  heroam_particle *h_stage = nullptr;
+  size_t cap_stage = 0;
   // current batch
   unsigned long long he_number = 0;
   uint32_t n_traj = 0;
@@ -257,6 +262,7 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
   cudaFree(ctx->d_counters);
   cudaFreeHost(ctx->h_bin_count);
   cudaFreeHost(ctx->h_counters);
+  cudaFreeHost(ctx->h_stage);
   for (int b = 0; b < N_BINS; ++b) {
     if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
     if (ctx->bin_done[b]) cudaEventDestroy(ctx->bin_done[b]);
@@ -652,30 +658,58 @@ extern "C" int heroam_gpu_simulate_flat(heroam_ctx *ctx, unsigned long long he_n
   return heroam_gpu_download(ctx, flat, results);
 }
 
+// records of trajectories [lo, hi) between the caller's per-trajectory arrays and the flat staging buffer
+static void stage_copy(heroam_particles *trajectories, const std::vector<size_t> &first, heroam_particle *stage, int lo,
+                       int hi, bool gather) {
+  for (int i = lo; i < hi; ++i) {
+    const size_t bytes = (size_t)trajectories[i].no * sizeof(heroam_particle);
+    if (gather) memcpy(stage + first[i], trajectories[i].particle, bytes);
+    else memcpy(trajectories[i].particle, stage + first[i], bytes);
+  }
+}
+
+static void stage_parallel(heroam_particles *trajectories, const std::vector<size_t> &first, heroam_particle *stage,
+                           int count, bool gather) {
+  // a copy of tens of bytes per trajectory is bound by memory latency: a few host threads for large batches
+  unsigned hw = std::thread::hardware_concurrency();
+  int n_threads = count < 65536 ? 1 : (int)(hw ? (hw > 16 ? 16 : hw) : 4);
+  if (n_threads <= 1) {
+    stage_copy(trajectories, first, stage, 0, count, gather);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_threads; ++t) {
+    const int lo = (int)((long long)count * t / n_threads), hi = (int)((long long)count * (t + 1) / n_threads);
+    pool.emplace_back(stage_copy, trajectories, std::cref(first), stage, lo, hi, gather);
+  }
+  for (auto &th : pool) th.join();
+}
+
 extern "C" int heroam_gpu_simulate_batch(heroam_ctx *ctx, unsigned long long he_number,
                                          heroam_particles *trajectories, int count, heroam_traj_result *results) {
   if (!ctx || (!trajectories && count > 0) || count < 0) return fail(HEROAM_E_ARG, "heroam_gpu_simulate_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
   std::vector<uint32_t> counts((size_t)count);
+  std::vector<size_t> first((size_t)count);
   size_t total = 0;
   for (int i = 0; i < count; ++i) {
     if (!trajectories[i].particle || trajectories[i].no == 0)
       return fail(HEROAM_E_ARG, "trajectory %d is empty", i);
     counts[i] = trajectories[i].no;
+    first[i] = total;
     total += counts[i];
   }
-  std::vector<heroam_particle> flat(total);
-  size_t at = 0;
-  for (int i = 0; i < count; ++i) {
-    memcpy(flat.data() + at, trajectories[i].particle, (size_t)counts[i] * sizeof(heroam_particle));
-    at += counts[i];
+  if (total > ctx->cap_stage) {
+    cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->cap_stage = 0;
+    CU(cudaMallocHost(&ctx->h_stage, total * sizeof(heroam_particle)));
+    ctx->cap_stage = total;
   }
-  int rc = heroam_gpu_simulate_flat(ctx, he_number, counts.data(), flat.data(), count, results);
+  stage_parallel(trajectories, first, ctx->h_stage, count, true);
+  int rc = heroam_gpu_simulate_flat(ctx, he_number, counts.data(), ctx->h_stage, count, results);
   if (rc) return rc;
-  at = 0;
-  for (int i = 0; i < count; ++i) {
-    memcpy(trajectories[i].particle, flat.data() + at, (size_t)counts[i] * sizeof(heroam_particle));
-    at += counts[i];
-  }
+  stage_parallel(trajectories, first, ctx->h_stage, count, false);
   return HEROAM_OK;
 }
 

@@ -29,6 +29,9 @@ HIST_N = 256
 HIST_T = 4096
 
 RESULT_DTYPE = np.dtype([("steps", "<u4"), ("status", "<u4"), ("n_flagged", "<u4"), ("time", "<f4")])
+#: numpy view of the reference's ``Particles`` header (simulation.h:53-57): no, index, Particle*
+PARTICLES_DTYPE = np.dtype([("no", "<u4"), ("index", "<u4"), ("particle", "<u8")])
+assert PARTICLES_DTYPE.itemsize == 16
 
 #: every symbol include/heroam_gpu.h declares
 ABI_SYMBOLS = (
@@ -278,6 +281,15 @@ class Engine:
         assert counts.flags.c_contiguous and flat.flags.c_contiguous and results.flags.c_contiguous
         self._check(self.lib.heroam_gpu_simulate_flat(self.handle, he_number, counts.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                       flat.ctypes.data, len(counts), results.ctypes.data))
+
+    def simulate_batch_inplace(self, he_number: int, particles: np.ndarray, results: np.ndarray) -> None:
+        """``heroam_gpu_simulate_batch`` on an array of the reference's ``Particles`` headers
+        (``PARTICLES_DTYPE``: no, index, pointer to that trajectory's records), in place."""
+        assert particles.dtype == PARTICLES_DTYPE and particles.flags.c_contiguous
+        assert results.dtype == RESULT_DTYPE and len(results) == len(particles)
+        self._check(self.lib.heroam_gpu_simulate_batch(self.handle, he_number,
+                                                       C.cast(particles.ctypes.data, C.POINTER(ParticlesC)),
+                                                       len(particles), results.ctypes.data))
 
     def sample_into(self, he_number: int, count: int, first_index: int, counts: np.ndarray, flat: np.ndarray) -> int:
         """``heroam_gpu_sample_flat`` into caller-owned buffers; returns the number of records

@@ -14,8 +14,9 @@ from .engine import HIST_N, HIST_T
 #: integer entries of a statistics dict that are summed across ranks
 SUM_KEYS = ("trajectories", "particles", "unmet_particles")
 HIST_KEYS = ("hist_n", "hist_traj_time", "hist_meet_time", "done")
-INFO_SUM_KEYS = ("trajectories", "particles", "particle_steps", "pair_steps", "inrange_steps", "passes",
-                 "kernel_launches")
+#: work counters of the run info that add up across ranks (passes and the timings stay the rank's own)
+INFO_SUM_KEYS = ("trajectories", "particles", "particle_steps", "pair_steps", "inrange_steps", "pair_skipped",
+                 "free_steps", "kernel_launches")
 
 
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:

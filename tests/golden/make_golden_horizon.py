@@ -40,11 +40,14 @@ from sphere_roaming_b200.types import make_config  # noqa: E402
 
 def run(ref, conf, he, table, counts, init, what):
     t0 = time.perf_counter()
-    final = ref.simulate(conf, he, table, counts, init, nthreads=0, dynamic=True)
+    # guarded: the reference itself never returns from a trajectory whose particles are all frozen with
+    # its `==` success criterion unmet (71 of 1e6 trajectories of C2) -- see ref_harness.c
+    final, dead = ref.simulate_guarded(conf, he, table, counts, init, nthreads=0, dynamic=True)
     dt = time.perf_counter() - t0
     ps = float(final["time"].astype(np.float64).sum()) / conf.dt
-    print(f"{what}: {len(counts)} trajectories, {ps:.3e} particle-steps in {dt:.1f} s ({ps / dt:.3e}/s)", flush=True)
-    return final
+    print(f"{what}: {len(counts)} trajectories, {ps:.3e} particle-steps in {dt:.1f} s ({ps / dt:.3e}/s), "
+          f"{int(dead.sum())} deadlocked in the reference", flush=True)
+    return final, dead
 
 
 def c2(table):
@@ -52,21 +55,21 @@ def c2(table):
     conf = make_config(number=4096, max_time=1.0e7)
     strict, release = RefOracle("strict"), RefOracle("release")
     counts, init = strict.initialize(conf, he, table)
-    final = run(strict, conf, he, table, counts, init, "C2 strict")
-    rel = run(release, conf, he, table, counts, init, "C2 release")
+    final, dead = run(strict, conf, he, table, counts, init, "C2 strict")
+    rel, _ = run(release, conf, he, table, counts, init, "C2 release")
     np.savez_compressed(os.path.join(HERE, "horizon_c2.npz"), he_number=np.int64(he), max_time=np.float32(conf.max_time),
-                        counts=counts, init=init, final=final, release_time=rel["time"], release_success=rel["success"],
-                        release_position=rel["position"])
+                        counts=counts, init=init, final=final, deadlocked=dead, release_time=rel["time"],
+                        release_success=rel["success"], release_position=rel["position"])
 
 
 def generic(table, name, he, number, max_time, **over):
     conf = make_config(number=number, max_time=max_time, **over)
     strict = RefOracle("strict")
     counts, init = strict.initialize(conf, he, table)
-    final = run(strict, conf, he, table, counts, init, name)
+    final, dead = run(strict, conf, he, table, counts, init, name)
     extra = {k: np.float32(v) for k, v in over.items()}
     np.savez_compressed(os.path.join(HERE, f"horizon_{name}.npz"), he_number=np.int64(he), max_time=np.float32(max_time),
-                        counts=counts, init=init, final=final, **extra)
+                        counts=counts, init=init, final=final, deadlocked=dead, **extra)
 
 
 def main():
