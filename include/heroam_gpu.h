@@ -94,11 +94,6 @@ typedef struct heroam_options {
                              (heroam_run_info.inrange_steps) at ~3 % cost; exact mode always counts   */
   int no_flight;          /* cross-check only: 1 = no free flight and no splitting, every moving particle is
                              integrated in full every step (results must not change)                  */
-  /* While a run is latency-bound (fewer trajectories in the integrate kernels than fill the GPU) the
-   * kernels of a pass run a time slice instead of a fixed number of steps, so that a pass lasts as long
-   * as the slice and not as long as its slowest chain of steps.                                       */
-  int no_time_slice;      /* cross-check only: 1 = fixed step segments throughout (results must not change) */
-  unsigned int pass_slice_us;       /* length of that slice in microseconds (0 = default)             */
 } heroam_options;
 
 typedef struct heroam_traj_result {

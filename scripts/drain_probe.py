@@ -15,18 +15,17 @@ table = synthetic_table()
 ref = None
 for setting in os.environ.get("SETTINGS", "off;on").split(";"):
     kw = {}
-    for k in ("HEROAM_DRAIN_PER_SM", "HEROAM_DRAIN_LIVE_PER_SM", "HEROAM_BULK_SLICE_CAP_US", "HEROAM_BULK_SEG_MULT", "HEROAM_NOSPLIT_MAX", "HEROAM_X_NOFAR", "HEROAM_X_NOEXACT", "HEROAM_BOOST_PER_SM"):
+    for k in ("HEROAM_DRAIN_PER_SM", "HEROAM_DRAIN_LIVE_PER_SM", "HEROAM_BULK_SLICE_CAP_US", "HEROAM_BULK_SEG_MULT", "HEROAM_NOSPLIT_MAX", "HEROAM_X_NOFAR", "HEROAM_X_NOEXACT", "HEROAM_LOOKAHEAD_BULK"):
         os.environ.pop(k, None)
     for tok in setting.split(","):
         if tok == "on": pass
         elif tok.startswith("base="): kw["segment_steps"] = int(tok[5:])
-        elif tok == "noslice": kw["no_time_slice"] = 1
-        elif tok.startswith("pus="): kw["pass_slice_us"] = int(tok[4:])
         elif tok.startswith("live="): os.environ["HEROAM_DRAIN_LIVE_PER_SM"] = tok[5:]
         elif tok.startswith("cap="): os.environ["HEROAM_BULK_SLICE_CAP_US"] = tok[4:]
         elif tok.startswith("mult="): os.environ["HEROAM_BULK_SEG_MULT"] = tok[5:]
         elif tok.startswith("nosplit="): os.environ["HEROAM_NOSPLIT_MAX"] = tok[8:]
         elif tok == "nofar": os.environ["HEROAM_X_NOFAR"] = "1"
+        elif tok.startswith("labulk="): os.environ["HEROAM_LOOKAHEAD_BULK"] = tok[7:]
         elif tok == "noexact": os.environ["HEROAM_X_NOEXACT"] = "1"
     with engine.Engine(make_config(number=N, max_time=MT), table, mode=MODE, **kw) as eng:
         if ref is None:

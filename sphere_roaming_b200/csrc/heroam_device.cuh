@@ -69,6 +69,9 @@ struct Consts {
   float max_time;    // :469
   int grid_len;      // :219 (clamped to INT_MAX on the host)
   uint32_t max_steps;   // steps until the float clock reaches max_time (host-iterated)
+  uint32_t clock_exact; // 1: after k steps the reference's clock (time += dt, k times) equals (float)k * dt for every
+                        // k <= max_steps (checked on the host): a flight may then set it at landing instead of
+                        // adding dt in every step
   // fast-mode folded constants
   float far2;        // squared distance beyond which a pair can neither feel force nor meet (with margin)
   float kick;        // acc_scale * half_dt
@@ -110,35 +113,6 @@ struct DevView {       // everything a kernel needs, passed by value
   unsigned long long nbr_cap;
   Counters *counters;
   uint32_t n_traj;
-  // Time slice of the integrate kernels in SM clock cycles (0 = none): a thread stops at the next
-  // step that is a multiple of SLICE_CHECK once its kernel has been running this long, whatever its
-  // segment says.  Used while a run is latency-bound, so that a pass lasts as long as the slice and
-  // not as long as the slowest chain of steps in it (results do not depend on where segments end).
-  long long slice_cycles;
-  // A time-sliced thread whose pairs are all out of reach, and provably stay so for at least this many
-  // steps, hands its trajectory back at the next check point: the re-analysis of the next pass will
-  // let it fly.  Set per pass by the host to twice the shortest flight on offer.
-  float far_exit_steps;
-};
-
-constexpr uint32_t SLICE_CHECK = 64;  // a multiple of RENORM_ALIGN: warps stay in phase
-
-// Bookkeeping of the time slice inside a step loop: one compare per step, one clock read per
-// SLICE_CHECK steps.
-struct SliceClock {
-  long long t0, budget;
-  uint32_t next_check;
-  __device__ __forceinline__ void start(long long slice_cycles, uint32_t steps) {
-    budget = slice_cycles;
-    t0 = slice_cycles ? clock64() : 0;
-    next_check = slice_cycles ? ((steps + SLICE_CHECK) & ~(SLICE_CHECK - 1u)) : 0xffffffffu;
-  }
-  // true: stop before the step with index `steps`
-  __device__ __forceinline__ bool expired(uint32_t steps) {
-    if (steps != next_check) return false;
-    next_check += SLICE_CHECK;
-    return clock64() - t0 >= budget;
-  }
 };
 
 // ---------------------------------------------------------------------------------

@@ -96,7 +96,6 @@ struct heroam_ctx {
   bool uploaded = false;
   heroam_run_info info;
   int sm_count = 0;
-  int clock_khz = 0;   // nominal SM clock (queried once: the attribute call is slow)
 };
 
 extern "C" int heroam_gpu_abi_version(void) { return HEROAM_ABI_VERSION; }
@@ -115,16 +114,19 @@ extern "C" const char *heroam_gpu_last_error(void) { return g_err; }
 // Steps until the reference's float clock reaches max_time, iterated exactly as the
 // reference accumulates it (particle->time += dt, simulation.c:507).  Returns false when
 // the clock stops advancing first: the reference would then loop forever (Q10).
-static bool clock_steps(float dt, float max_time, uint32_t *steps_out) {
+static bool clock_steps(float dt, float max_time, uint32_t *steps_out, uint32_t *exact_out) {
   float t = 0.0f;
   uint64_t k = 0;
+  bool exact = true;  // is the accumulated clock the product (float)k * dt all the way?
   while (t < max_time) {
     const float next = t + dt;
     if (!(next > t)) return false;
     t = next;
     if (++k >= 0xfffffff0ull) return false;
+    exact = exact && k < (1ull << 24) && t == (float)k * dt;
   }
   *steps_out = (uint32_t)k;
+  *exact_out = exact ? 1u : 0u;
   return true;
 }
 
@@ -140,7 +142,7 @@ static int make_consts(const heroam_config &conf, unsigned long long he_number, 
   c.max_time = conf.max_time;
   c.grid_len = conf.force_grid_length > 0x7fffffffL ? 0x7fffffff : (int)conf.force_grid_length;
   if (!(conf.dt > 0.0f)) return fail(HEROAM_E_ARG, "dt must be positive (got %g)", (double)conf.dt);
-  if (!clock_steps(conf.dt, conf.max_time, &c.max_steps))
+  if (!clock_steps(conf.dt, conf.max_time, &c.max_steps, &c.clock_exact))
     return fail(HEROAM_E_CLOCK,
                 "dt=%g cannot advance a float clock up to max_time=%g: the reference's loop would never end",
                 (double)conf.dt, (double)conf.max_time);
@@ -188,7 +190,6 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   ctx->conf = *conf;
   ctx->opt = options;
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
   const int rc = init_context(ctx, force_list);
   if (rc) {  // whatever was created so far is released; the error message stays
     heroam_gpu_destroy(ctx);
@@ -347,8 +348,6 @@ static DevView make_view(heroam_ctx *ctx, const Consts &c) {
   v.nbr_cap = ctx->nbr_cap;
   v.counters = ctx->d_counters;
   v.n_traj = ctx->n_traj;
-  v.slice_cycles = 0;
-  v.far_exit_steps = 3.0e38f;
   return v;
 }
 
@@ -415,48 +414,21 @@ static int env_int(const char *name, int fallback) {
   return e && *e ? atoi(e) : fallback;
 }
 
-// SM clock cycles of a time slice of `us` microseconds (at the nominal clock: a slice is a
-// scheduling quantum, not a measurement)
-static long long slice_cycles_of(const heroam_ctx *ctx, unsigned us) {
-  return (long long)us * (long long)ctx->clock_khz / 1000;
-}
-
-// What a pass is launched with under regime rg: segments for the resolve kernel, the time slice and
-// the give-up distance for the integrate kernels.
-static Segments pass_segments(const heroam_ctx *ctx, const Regime &rg, DevView &v) {
-  // Time slices only while latency-bound.  While the GPU is full, letting the unsplit narrow bins run for
-  // the length of a pass was measured to cost 30 % on a 4e6-trajectory run: a trajectory that stays in a
-  // full kernel pays full steps long after a re-analysis would have split it or let it fly.
-  const bool sliced = rg.draining && !ctx->opt.no_time_slice && !ctx->opt.no_flight;
-  Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx), sliced);
+// What a pass is launched with under regime rg.
+static Segments pass_segments(const heroam_ctx *ctx, const Regime &rg) {
+  Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
   sg.free_stride = ctx->free_stride;
   sg.no_flight = ctx->opt.no_flight ? 1u : 0u;
-  v.slice_cycles = 0;
-  v.far_exit_steps = 3.0e38f;
-  if (!sliced) return sg;
-  v.slice_cycles = slice_cycles_of(ctx, ctx->opt.pass_slice_us ? ctx->opt.pass_slice_us : 3000u);
-  // a flight step is ~60 cycles of dependent instructions: flights as long as the slice
-  const long long fit = v.slice_cycles / 64;
-  if (fit > (long long)sg.flight_max) sg.flight_max = fit > 0x40000000ll ? 0x40000000u : (uint32_t)fit;
-  // give up a slice only for a flight at least twice as long as the shortest one on offer
-  v.far_exit_steps = 2.0f * (float)sg.of_bin[BIN_FREE + 1] + 64.0f;
   return sg;
 }
 
-// Decide the regime of the next pass from the populations the resolve kernel just reported.
-// can_refill: free slots would still be filled with new trajectories (streaming pool).
-static void update_regime(const heroam_ctx *ctx, Regime &rg, bool can_refill) {
+// Decide the regime of the next pass from the populations the resolve kernel just reported: fewer
+// trajectories in the full kernels than fill the GPU once means latency-bound from here on.
+static void update_regime(const heroam_ctx *ctx, Regime &rg) {
   uint64_t in_kernels = 0;
   for (int b = 1; b < N_BINS; ++b)
     if (b < BIN_FREE || b >= BIN_CORE) in_kernels += ctx->h_bin_count[b];
-  if (ctx->opt.no_time_slice) {
-    rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
-  } else {
-    // the drain policy does not split narrow trajectories, so what it would put into the full kernels
-    // is every live trajectory: switch when those fit the GPU at once
-    const int live_per_sm = env_int("HEROAM_DRAIN_LIVE_PER_SM", 400);  // experiments only
-    rg.draining = !can_refill && ctx->h_bin_count[LIVE_SLOT] <= (uint64_t)ctx->sm_count * live_per_sm;
-  }
+  rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
 }
 
 // R: arithmetic of the resolve steps, P: of the integrate kernels
@@ -466,13 +438,16 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, 
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
   if (bin >= BIN_FREE && bin < BIN_CORE) {
-    k_free_flight<P><<<(cnt + 127) / 128, 128, 0, s>>>(v, ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride, cnt);
+    const uint2 *flyers = ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride;
+    if (v.c.clock_exact) k_free_flight<P, true><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
+    else k_free_flight<P, false><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
     CU(cudaGetLastError());
     return HEROAM_OK;
   }
   const int width = bin >= BIN_CORE ? bin - BIN_CORE : bin;  // the core of a split trajectory runs in the kernel of its size
   static const bool lookahead_on = !(getenv("HEROAM_LOOKAHEAD") && atoi(getenv("HEROAM_LOOKAHEAD")) == 0);
-  if (draining && lookahead_on && width >= 2 && width <= 4) {  // latency-bound: prefetch the table two steps ahead
+  const int lookahead_bulk = env_int("HEROAM_LOOKAHEAD_BULK", 0);  // experiments only: widths <= this always prefetch
+  if ((draining || width <= lookahead_bulk) && lookahead_on && width >= 2 && width <= 4) {  // latency-bound: prefetch the table two steps ahead
     if (width == 2) k_integrate_thread<2, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
     else if (width == 3) k_integrate_thread<3, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
     else k_integrate_thread<4, P, true><<<grid, INTEGRATE_TPB, 0, s>>>(v, list, cnt);
@@ -546,7 +521,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
-    const Segments sg = pass_segments(ctx, rg, v);
+    const Segments sg = pass_segments(ctx, rg);
     if (lists.count)
       k_resolve_and_bin<R, H><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list,
                                                                                ctx->d_free_list, lists);
@@ -570,7 +545,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     uint64_t live = 0;
     for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
     if (live == 0) break;
-    update_regime(ctx, rg, false);
+    update_regime(ctx, rg);
     ctx->info.passes++;
     CU(cudaEventRecord(ctx->ev_i0, ctx->main));
     for (int b = 1; b < N_BINS; ++b) {

@@ -274,16 +274,10 @@ struct Segments {
                           // the short free-flight tier would only slow per-pass progress
   uint32_t no_flight;     // 1: per-step capture -- every particle's record must be current at every step
                           // boundary, so nobody flies and nothing is split off
-  uint32_t flight_max;    // != 0: a whole-trajectory flight of the medium or long tier takes min(horizon, flight_max)
-                          // steps instead of the tier's fixed length (the tier is then only the list the flyers
-                          // are put on): the long flights are few, and they are the pairs whose chains end a run
   uint32_t nosplit_max;   // trajectories with at most this many moving particles are not split into core and loners
-                          // (a core advances one bounded window per pass; unsplit it runs a whole time slice)
 };
 
-// sliced: the integrate kernels of the pass run a time slice (DevView::slice_cycles), so the segments
-// of the narrow bins are only upper bounds; otherwise (cross-check) fixed step segments throughout.
-__host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split_window_max, bool sliced) {
+__host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split_window_max) {
   Segments sg;
   auto scaled = [base](uint32_t num, uint32_t den) { uint32_t v = (uint32_t)((unsigned long long)base * num / den); return v ? v : 1u; };
   sg.of_bin[0] = base;
@@ -308,22 +302,13 @@ __host__ inline Segments make_segments(uint32_t base, bool drain, uint32_t split
     sg.of_bin[BIN_SMEM16] = scaled(1, 8);
     sg.of_bin[BIN_WARP1] = sg.of_bin[BIN_WARP2] = sg.of_bin[BIN_WARP4] = scaled(1, 8);
   }
-  if (sliced) {
-    // The integrate kernels run a time slice (DevView::slice_cycles): a pass then lasts as long as
-    // the slice whatever the bins in it, every trajectory advancing at its own chain latency, and
-    // the segments are only upper bounds.  The warp bins keep theirs: their partner lists are built
-    // for the segment, and the reach bound grows with its length.
-    for (int b = 2; b <= HYBRID_MAX_A; ++b) sg.of_bin[b] = 1u << 20;
-    sg.of_bin[BIN_SMEM16] = 1u << 20;
-  }
   // free flight: ~73 ns per step; the short tier is dropped while draining (schedule_segment)
   sg.of_bin[BIN_FREE + 0] = scaled(1, 4);
   sg.of_bin[BIN_FREE + 1] = scaled(2, 1);
   // While draining a pass lasts as long as its slowest kernel, and every trajectory advances one
   // segment per pass: a long tier of 8x (65 536 steps x 73 ns = 4.8 ms for a hundred flyers) would hold
   // up the thousands of two-particle trajectories whose segment takes half of that.
-  sg.of_bin[BIN_FREE + 2] = (drain && !sliced) ? scaled(4, 1) : scaled(8, 1);
-  sg.flight_max = sliced ? scaled(8, 1) : 0u;
+  sg.of_bin[BIN_FREE + 2] = drain ? scaled(4, 1) : scaled(8, 1);
   // split trajectories: core and loners advance by the same fixed window.  The reach bound grows
   // with the square of the window (possible acceleration), so beyond split_window_max =
   // O(sqrt(m / f_max) / dt) everything would look linked to everything.
@@ -344,7 +329,6 @@ __host__ inline Segments make_capture_segments(uint32_t chunk) {
   for (int b = 0; b < N_BINS; ++b) sg.of_bin[b] = chunk;
   sg.free_stride = 0;
   sg.drain = 0;
-  sg.flight_max = 0;
   sg.nosplit_max = 0;
   sg.no_flight = 1;
   return sg;
@@ -627,9 +611,7 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
   const uint32_t horizon = free_flight_horizon(v, m);
   for (int tier = 2; tier >= (sg.drain ? 1 : 0); --tier)
     if (horizon >= sg.of_bin[BIN_FREE + tier]) {
-      const uint32_t length = (sg.flight_max && tier >= 1) ? (horizon < sg.flight_max ? horizon : sg.flight_max)
-                                                           : sg.of_bin[BIN_FREE + tier];
-      m.step_stop = clip(m.steps + length);
+      m.step_stop = clip(m.steps + sg.of_bin[BIN_FREE + tier]);
       m.status = ST_FLYING;
       out.fly_tier = tier;
       out.fly_first = 0;
@@ -822,8 +804,9 @@ __device__ __forceinline__ void load_flyer(const DevView &v, const TrajMeta &m, 
 
 // N flyers of ONE trajectory (same from / until / clock) advanced together: their steps are
 // independent, so interleaving them hides each other's dependency chains.  Per flyer exactly
-// the operations of the full kernels, in their order.
-template <class P, int N>
+// the operations of the full kernels, in their order.  CLOCK_PRODUCT (Consts::clock_exact): the
+// clock is set at the end, (float)until * dt, instead of being advanced in every step.
+template <class P, int N, bool CLOCK_PRODUCT>
 __device__ __forceinline__ void fly_together(const Consts &c, Flyer (&fl)[N]) {
   uint32_t k = fl[0].from;
   const uint32_t until = fl[0].until;
@@ -834,30 +817,31 @@ __device__ __forceinline__ void fly_together(const Consts &c, Flyer (&fl)[N]) {
     for (; k < until && (k & (P::renorm_every - 1u)) != 0u; ++k) {
 #pragma unroll
       for (int i = 0; i < N; ++i) advance_orientation<P>(c, fl[i].w, fl[i].q, renorm_at<P>(k));
-      time = __fadd_rn(time, c.dt);
+      if (!CLOCK_PRODUCT) time = __fadd_rn(time, c.dt);
     }
     for (; k + P::renorm_every <= until; k += P::renorm_every) {
 #pragma unroll
       for (uint32_t u = 0; u < P::renorm_every; ++u) {
 #pragma unroll
         for (int i = 0; i < N; ++i) advance_orientation<P>(c, fl[i].w, fl[i].q, u + 1u == P::renorm_every);
-        time = __fadd_rn(time, c.dt);
+        if (!CLOCK_PRODUCT) time = __fadd_rn(time, c.dt);
       }
     }
   }
   for (; k < until; ++k) {
 #pragma unroll
     for (int i = 0; i < N; ++i) advance_orientation<P>(c, fl[i].w, fl[i].q, renorm_at<P>(k));
-    time = __fadd_rn(time, c.dt);
+    if (!CLOCK_PRODUCT) time = __fadd_rn(time, c.dt);
   }
+  if (CLOCK_PRODUCT && until > fl[0].from) time = __fmul_rn(__uint2float_rn(until), c.dt);
 #pragma unroll
   for (int i = 0; i < N; ++i) fl[i].time = time;
 }
 
-template <class P>
+template <class P, bool CLOCK_PRODUCT>
 __device__ __forceinline__ void fly_alone(const Consts &c, Flyer &fl) {
   Flyer one[1] = {fl};
-  fly_together<P, 1>(c, one);
+  fly_together<P, 1, CLOCK_PRODUCT>(c, one);
   fl = one[0];
 }
 
@@ -874,14 +858,14 @@ __device__ __forceinline__ void land_flyer(const Consts &c, const Flyer &fl) {
   p->time = fl.time;
 }
 
-template <class P>
+template <class P, bool CLOCK_PRODUCT>
 __global__ void __launch_bounds__(128) k_free_flight(DevView v, const uint2 *__restrict__ list, uint32_t count) {
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= count) return;
   Flyer fl;
   const uint2 e = list[item];
   load_flyer<P>(v, v.meta[e.x], e.y, fl);
-  fly_alone<P>(v.c, fl);
+  fly_alone<P, CLOCK_PRODUCT>(v.c, fl);
   land_flyer<P>(v.c, fl);
 }
 
@@ -921,36 +905,12 @@ __device__ __forceinline__ void rebuild_forces(const DevView &v, const float (&r
 // (all of it drain) takes 4.2 s with it, 4.65 s without, 5.1 s with the one-step look-ahead
 // into registers it replaced (DESIGN.md section 7 has the other variants).
 // ---------------------------------------------------------------------------------
-// free_flight_horizon on the state a kernel holds in registers (same bound, same constants): the number
-// of steps for which no pair can come within reach; only meaningful when every pair is out of reach now.
-template <int A, class P>
-__device__ __forceinline__ float flight_horizon_now(const Consts &c, const float (&r)[A][3], const float (&w)[A][3]) {
-  float reach[A];
-#pragma unroll
-  for (int s = 0; s < A; ++s) {
-    float wr[3];
-    unscale_w<P>(c, w[s], wr);
-    reach[s] = sqrtf(wr[0] * wr[0] + wr[1] * wr[1] + wr[2] * wr[2]) * c.radius * c.dt * 1.01f + 2.0e-6f * c.radius;
-  }
-  const float d_far = sqrtf(c.far2) * 1.00001f + 1.0e-3f;
-  float horizon = 4.0e9f;
-#pragma unroll
-  for (int j = 0; j < A - 1; ++j)
-#pragma unroll
-    for (int k = j + 1; k < A; ++k) {
-      const float dx = r[j][0] - r[k][0], dy = r[j][1] - r[k][1], dz = r[j][2] - r[k][2];
-      const float gap = sqrtf(dx * dx + dy * dy + dz * dz) - d_far;
-      horizon = fminf(horizon, gap / (reach[j] + reach[k]) * 0.999f - 2.0f);
-    }
-  return horizon;
-}
-
 // One segment of a trajectory with A moving particles, by one thread: loads the records, runs
 // steps [m.steps, m.step_stop) or up to a meeting, leaves the records (clean, or mid-step) and
 // updates m (steps, clock, status).  Returns the number of steps completed.
 template <int A, class P, bool LOOKAHEAD>
 __device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, TrajMeta &m, const unsigned sink_addr,
-                                                             unsigned long long &inrange_total, const long long slice_cycles) {
+                                                             unsigned long long &inrange_total) {
   const Consts &c = v.c;
   heroam_particle *rec[A];
   float q[A][4], w[A][3], r[A][3], f[A][3], hk[A][3], wh[A][3], r_old[A][3];
@@ -974,16 +934,7 @@ __device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, T
   float pos_prev[LOOKAHEAD ? NP + 1 : 1];
 #pragma unroll
   for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
-  SliceClock slice;
-  slice.start(slice_cycles, steps);
-  float dmin_last = 0.0f;
   while (steps < m.step_stop) {
-    // end of the time slice -- or, at the same check points, every pair far out of reach: hand the
-    // trajectory back for re-analysis (it will fly) instead of spending full steps on it
-    if (steps == slice.next_check) {
-      if (A >= 2 && dmin_last > c.far2 && flight_horizon_now<A, P>(c, r, w) >= v.far_exit_steps) break;
-      if (slice.expired(steps)) break;
-    }
     const bool rn = renorm_at<P>(steps);
     // first half kick + drift (simulation.c:478-490)
 #pragma unroll
@@ -1038,7 +989,6 @@ __device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, T
       asm volatile("cp.async.wait_group 3;");
     }
     if (dmin < c.icd2) { met = true; break; }
-    dmin_last = dmin;
     // second half kick (:496-509); velocity and clock fields are written at the end
 #pragma unroll
     for (int s = 0; s < A; ++s) {
@@ -1079,7 +1029,7 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
   if (item < count) {
     const uint32_t t = list[item];
     TrajMeta m = v.meta[t];
-    done_steps = integrate_thread_segment<A, P, LOOKAHEAD>(v, m, sink_addr, inrange_total, v.slice_cycles);
+    done_steps = integrate_thread_segment<A, P, LOOKAHEAD>(v, m, sink_addr, inrange_total);
     v.meta[t] = m;
   }
   const unsigned long long ds = warp_sum_u64(done_steps);
@@ -1133,10 +1083,7 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_hybrid(DevView v, const 
     uint32_t steps = m.steps;
     float time = m.time;
     bool met = false;
-    SliceClock slice;
-    slice.start(v.slice_cycles, steps);
     while (steps < m.step_stop) {
-      if (slice.expired(steps)) break;
       const bool rn = renorm_at<P>(steps);
 #pragma unroll
       for (int s = 0; s < A; ++s) {
@@ -1297,10 +1244,7 @@ __global__ void __launch_bounds__(SMEM_TPB) k_integrate_smem(DevView v, const ui
     uint32_t steps = m.steps;
     float time = m.time;
     bool met = false;
-    SliceClock slice;
-    slice.start(v.slice_cycles, steps);
     while (steps < m.step_stop) {
-      if (slice.expired(steps)) break;
       const bool rn = renorm_at<P>(steps);
       // first half kick + drift
 #pragma unroll 2
@@ -1488,10 +1432,7 @@ k_integrate_warp(DevView v, const uint32_t *__restrict__ list, uint32_t count, b
   float time = m.time;
   bool met = false;
   unsigned long long inrange_total = 0;
-  SliceClock slice;
-  slice.start(v.slice_cycles, steps);
   while (steps < m.step_stop) {
-    if (__any_sync(0xffffffffu, slice.expired(steps))) break;  // one trajectory per warp: the lanes leave together
     const bool rn = renorm_at<P>(steps);  // one trajectory per warp: uniform
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
@@ -1566,10 +1507,7 @@ __global__ void k_integrate_records(DevView v, const uint32_t *__restrict__ list
   const uint32_t *act = v.act + m.first;
   const uint32_t a = m.n_active;
   unsigned long long done_steps = 0, inrange_total = 0;
-  SliceClock slice;
-  slice.start(v.slice_cycles, m.steps);
   while (m.steps < m.step_stop) {
-    if (slice.expired(m.steps)) break;
     for (uint32_t s = 0; s < a; ++s) {
       heroam_particle *p = base + act[s];
       float hk[3], wh[3], q[4], r[3];

@@ -505,7 +505,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
   for (;;) {
     CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
-    const Segments sg = pass_segments(ctx, rg, v);
+    const Segments sg = pass_segments(ctx, rg);
     if (lists.count)
       k_pool_resolve<R, H><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count,
                                                                            ctx->d_bin_list, ctx->d_free_list, lists);
@@ -534,7 +534,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
     // a free slot claims a new trajectory in every pass while there are any: live < slots means none are left,
     // and from then on only the slots listed as live need a visit
     if (ctx->h_bin_count[LIVE_SLOT] < slots) pool.refill = 0;
-    update_regime(ctx, rg, pool.refill != 0);
+    update_regime(ctx, rg);
     if (!pool.refill) {
       lists.in = lists.out;
       lists.count = ctx->h_bin_count[LIVE_SLOT];

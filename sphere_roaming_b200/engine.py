@@ -14,7 +14,7 @@ import numpy as np
 from .types import PARTICLE_DTYPE, Config, ParticlesC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libheroam_gpu.so")
+LIB_PATH = os.environ.get("HEROAM_LIB") or os.path.join(_HERE, "libheroam_gpu.so")  # the env override: A/B builds only
 
 MODE_EXACT = 0
 MODE_FAST = 1
@@ -72,8 +72,6 @@ class Options(C.Structure):
         ("pool_slots", C.c_uint),
         ("count_work", C.c_int),
         ("no_flight", C.c_int),
-        ("no_time_slice", C.c_int),
-        ("pass_slice_us", C.c_uint),
     ]
 
 
@@ -189,8 +187,7 @@ class Engine:
     """One GPU context (``heroam_gpu_create``): force table resident on the device."""
 
     def __init__(self, conf: Config, table: np.ndarray, device: int = 0, mode="exact", segment_steps: int = 0,
-                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0, no_flight: int = 0,
-                 no_time_slice: int = 0, pass_slice_us: int = 0):
+                 max_steps: int = 0, wide_kernel: int = 0, pool_slots: int = 0, count_work: int = 0, no_flight: int = 0):
         self.lib = load_library()
         self.conf = conf
         table = np.ascontiguousarray(table, dtype=np.float32)
@@ -204,8 +201,6 @@ class Engine:
         opt.pool_slots = pool_slots
         opt.count_work = count_work
         opt.no_flight = no_flight
-        opt.no_time_slice = no_time_slice
-        opt.pass_slice_us = pass_slice_us
         h = C.c_void_p()
         self._check(self.lib.heroam_gpu_create(C.byref(conf), table.ctypes.data_as(C.POINTER(C.c_float)), device,
                                                C.byref(opt), C.byref(h)))

@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_header():
-    # heroam_options: int, uint, ull, int, uint, int, int, int, uint; heroam_traj_result: 16 bytes
-    assert C.sizeof(engine.Options) == 40
+    # heroam_options: int, uint, ull, int, uint, int, int; heroam_traj_result: 16 bytes
+    assert C.sizeof(engine.Options) == 32
     assert engine.RESULT_DTYPE.itemsize == 16
     assert C.sizeof(engine.RunInfo) == 16 * 8
     assert C.sizeof(engine.Stats) == 8 * (2 + 256 + 4096 + 4096 + 8 + 1 + 1) + C.sizeof(engine.RunInfo)

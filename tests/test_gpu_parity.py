@@ -52,17 +52,15 @@ def test_exact_mode_dense_droplet_golden(need_gpu, table, golden_traj):
     assert_records_equal(got, g["dense_final"], "dense droplet final state")
 
 
-@pytest.mark.parametrize("segment,no_slice", [(0, 0), (257, 0), (0, 1), (257, 1)])
-def test_exact_mode_matches_oracle_at_scale(need_gpu, port, table, segment, no_slice):
+@pytest.mark.parametrize("segment", [0, 257])
+def test_exact_mode_matches_oracle_at_scale(need_gpu, port, table, segment):
     """4096 Philox-sampled trajectories (config C2's physics; the per-trajectory
-    cross-check block), 1e5 steps, every record, outcome and work counter -- with time-sliced
-    passes (a batch this small is latency-bound from the second pass on) and with fixed step
-    segments throughout."""
+    cross-check block), 1e5 steps, every record, outcome and work counter."""
     n, max_time = 4096, 1.0e5
     conf = make_config(number=n, max_time=max_time)
     counts, init = port.sample(conf, HE, table, n, source="philox")
     want, wres, wctr = port.simulate(conf, HE, table, counts, init, want_counters=True)
-    with engine.Engine(conf, table, mode="exact", segment_steps=segment, no_time_slice=no_slice) as eng:
+    with engine.Engine(conf, table, mode="exact", segment_steps=segment) as eng:
         got, res = eng.simulate(HE, counts, init)
         info = eng.run_info()
     assert_records_equal(got, want, "final records")
@@ -185,9 +183,8 @@ def test_free_flight_and_splitting_change_nothing(need_gpu, table, mode):
     assert np.array_equal(res_a, res_b)
     assert with_flight.tobytes() == without.tobytes()
     assert info["particle_steps"] == info_b["particle_steps"] and info["pair_steps"] == info_b["pair_steps"]
-    # time-sliced passes against fixed step segments throughout, and with slices cut very differently
-    # (they end by the SM clock, so the cuts also differ from run to run)
-    for kw in (dict(no_time_slice=1), dict(pass_slice_us=100), dict(pass_slice_us=20000, segment_steps=3000)):
+    # segments cut very differently
+    for kw in (dict(segment_steps=3000), dict(segment_steps=100000)):
         with engine.Engine(conf, table, mode=mode, **kw) as eng:
             other, res_c = eng.simulate(HE, counts, init)
             info_c = eng.run_info()
