@@ -232,7 +232,7 @@ def reference_arm(args, table):
 #: flops of one free-flight particle-step as the fast kernels execute it: the increment w' (x) q
 #: (4 x (mul + 2 fma + add) = 24), the renormalisation (|q|^2: mul + 3 fma = 7, rsqrt 1, 4 mul) and the
 #: clock (1); the relaxed mode renormalises after every 8th step only
-FREE_STEP_FLOPS = {"fast": 37.0, "fast_relaxed": 24.0 + 1.0 + 12.0 / 8.0, "exact": 37.0}
+FREE_STEP_FLOPS = {"fast": 37.0, "fast_relaxed": 24.0 + 1.0 + 12.0 / 8.0, "exact": 37.0, "fast_closed": 0.0}
 
 
 def flop_model(info):
@@ -423,6 +423,21 @@ def gpu_arm(args, table):
                            "after every 8th step; its own position tolerance (DESIGN.md section 4)")
         eng.set_mode(args.mode)
 
+    # ---- closed-form free flight (opt-in), for the record -------------------------------------------
+    closed = None
+    if args.mode == "fast" and args.closed_step:
+        eng.set_mode("fast_closed")
+        k_cl = max(1, min(K, args.closed_step))
+        f, n = block(W, k_cl)
+        flush.fill_(3)
+        barrier()
+        st = eng.run_stats(HE, n, first_index=f)
+        closed = summarise(st["info"], inrange_ratio, "fast_closed")
+        closed["note"] = (f"HEROAM_MODE_FAST_CLOSED (opt-in): {k_cl} of the K steps as one run with every free flight taken as one "
+                          "rotation instead of step by step; particle-steps count the steps advanced, not instructions -- "
+                          "roofline_frac charges nothing for a flight step; its own tolerance row (DESIGN.md section 4)")
+        eng.set_mode(args.mode)
+
     # ---- the other BASELINE.json configurations ------------------------------------------------------
     extras = {}
     if args.extras:
@@ -543,6 +558,7 @@ def gpu_arm(args, table):
                          "integrate_share_of_step": integ_s / dev_s, "resolve_share_of_step": resolve_s / dev_s},
             "exact_mode": exact,
             "relaxed_mode": relaxed,
+            "closed_mode": closed,
             "outcomes": None if merged is None else {"success": int(merged["done"][0]), "max_time": int(merged["done"][1]),
                                                      "deadlock": int(merged["done"][2]), "trajectories": int(merged["trajectories"])},
         }
@@ -569,12 +585,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1000000, help="trajectories per GPU per step (C2: 1e6)")
     ap.add_argument("--max-time", type=float, default=1.0e7)
-    ap.add_argument("--mode", default="fast", choices=["fast", "exact", "fast_relaxed"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact", "fast_relaxed", "fast_closed"])
     ap.add_argument("--segment", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end arm (0 = all K)")
     ap.add_argument("--warmup-e2e", type=int, default=1)
     ap.add_argument("--exact-step", type=int, default=1)
     ap.add_argument("--relaxed-step", type=int, default=4, help="steps of the relaxed-mode run (0 = skip)")
+    ap.add_argument("--closed-step", type=int, default=4, help="steps of the closed-form-flight run (0 = skip)")
     ap.add_argument("--extras", type=int, default=1, help="0 = skip the c2_single_run / c3 / c4_sweep / c5_slice / t_large legs")
     ap.add_argument("--c2-number", type=int, default=1000000)
     ap.add_argument("--c3-number", type=int, default=10000)

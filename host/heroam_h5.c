@@ -32,7 +32,7 @@
 #define SUPERBLOCK_BYTES 96u
 #define HEAP_FREE_NULL 1ull /* "no free block" marker of a local heap */
 
-static char g_h5err[256] = "";
+static _Thread_local char g_h5err[256] = "";  /* written from the per-GPU host threads */
 const char *heroam_h5_last_error(void) { return g_h5err; }
 static int h5fail(const char *fmt, ...) {
   va_list ap;

@@ -22,6 +22,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <sys/types.h>
+#include <time.h>
 
 #include "../include/heroam_gpu.h"
 #include "heroam_h5.h"
@@ -108,10 +109,17 @@ static int simulate_for_number(int helium_number, const heroam_config *conf, con
       failed |= 1;
     }
   }
-  if (failed) return 1;
   char path[96];
   snprintf(path, sizeof path, "./results/particlefile_%d", helium_number);
-  heroam_write_particlefile(path, all, number);
+  if (!failed && heroam_write_particlefile(path, all, number)) {
+    perror(path);
+    failed = 1;
+  }
+  if (failed) { /* whatever the GPUs that did succeed allocated is released */
+    for (int i = 0; i < number; ++i) heroam_gpu_free_particles(all + i);
+    free(all);
+    return 1;
+  }
   /* integration stage: the loop of main.c:76-78 */
 #pragma omp parallel for num_threads(n_gpus) schedule(static, 1) reduction(| : failed)
   for (int g = 0; g < n_gpus; ++g) {
@@ -124,7 +132,10 @@ static int simulate_for_number(int helium_number, const heroam_config *conf, con
     }
   }
   snprintf(path, sizeof path, "./results/particlefile_after_%d", helium_number);
-  if (!failed) heroam_write_particlefile(path, all, number);
+  if (!failed && heroam_write_particlefile(path, all, number)) {
+    perror(path);
+    failed = 1;
+  }
   for (int i = 0; i < number; ++i) heroam_gpu_free_particles(all + i);
   free(all);
   return failed;
@@ -191,7 +202,17 @@ int main(int argc, char *argv[]) {
   }
   struct stat st;
   if (stat("./results", &st) == -1) mkdir("./results", 0700);
-  heroam_write_forcelist("./results/forcelist.txt", &conf, table, count);
+  if (heroam_write_forcelist("./results/forcelist.txt", &conf, table, count)) {
+    perror("./results/forcelist.txt");
+    free(table);
+    return 1;
+  }
+  /* seed = 0 means "seed from the clock" (simulation.c:283-286).  Resolved ONCE here, so that every GPU
+   * samples from the same Philox stream, and reported, so that the run can be repeated. */
+  if (conf.seed == 0) {
+    conf.seed = (long)time(NULL);
+    printf("seed = 0: seeding from the clock, seed = %ld\n", conf.seed);
+  }
 
   const int n_gpus = n_gpus_wanted();
   if (n_gpus < 1) {
@@ -206,6 +227,9 @@ int main(int argc, char *argv[]) {
   for (int g = 0; g < n_gpus; ++g)
     if (heroam_gpu_create(&conf, table, g, &opt, &ctx[g])) {
       fprintf(stderr, "GPU %d: %s\n", g, heroam_gpu_last_error());
+      for (int h = 0; h < g; ++h) heroam_gpu_destroy(ctx[h]);
+      free(ctx);
+      free(table);
       return 1;
     }
   const int stats_only = getenv("HEROAM_STATS") && atoi(getenv("HEROAM_STATS")) != 0;

@@ -66,7 +66,16 @@ enum {
    * mirror the reference's one for one: positions agree with the strict reference to ~2e-3 A
    * (median, after 2e5 steps) instead of ~2e-5 A.  Exit times and success patterns meet the
    * same bounds as HEROAM_MODE_FAST.  Opt-in. */
-  HEROAM_MODE_FAST_RELAXED = 3
+  HEROAM_MODE_FAST_RELAXED = 3,
+  /* HEROAM_MODE_FAST with every free flight taken as ONE rotation instead of step by step (without
+   * force a particle turns rigidly about its fixed axis: the exact solution of the map the reference
+   * iterates).  Three quarters of all particle-steps of the repository configuration are free flight,
+   * so this is about twice as fast again -- but the per-step roundings of the reference are not
+   * reproduced during flights, so positions agree with the strict reference only to the size of its own
+   * rounding walk, and results depend (in the last bits, not statistically) on how a run is cut into
+   * passes: a trajectory is reproducible for the same run, not across batch or pool sizes.  Opt-in;
+   * its own tolerance row in tests/horizon_common.py. */
+  HEROAM_MODE_FAST_CLOSED = 4
 };
 
 /* How a trajectory left the step loop (heroam_traj_result.status). */
@@ -145,7 +154,10 @@ int heroam_gpu_device_count(void);
 const char *heroam_gpu_last_error(void);
 
 /* Context: one per GPU.  Uploads the force table (conf->force_grid_length floats,
- * main.c:130) once; conf and force_list are copied, the caller may free them. */
+ * main.c:130) once; conf and force_list are copied, the caller may free them.
+ * conf->seed == 0 means "seed from the clock", as in the reference (simulation.c:283-286):
+ * it is resolved to time(NULL) here, once per context -- a caller that drives several
+ * contexts as one run should resolve it itself and pass the same non-zero seed to all. */
 int heroam_gpu_create(const heroam_config *conf, const float *force_list, int device,
                       const heroam_options *opt /* NULL = defaults (exact mode) */,
                       heroam_ctx **out);

@@ -119,6 +119,7 @@ struct DevView {       // everything a kernel needs, passed by value
 // arithmetic policies
 // ---------------------------------------------------------------------------------
 struct Exact {
+  static constexpr bool closed_flight = false; // free flight one step at a time, as the reference takes them
   static constexpr unsigned renorm_every = 1;  // steps between renormalisations of the orientation
   static constexpr bool exact = true;
   static constexpr bool turbo = false;
@@ -150,6 +151,7 @@ struct Exact {
 };
 
 struct Fast {
+  static constexpr bool closed_flight = false;
   static constexpr unsigned renorm_every = 1;
   static constexpr bool exact = false;
   static constexpr bool turbo = false;
@@ -180,6 +182,12 @@ struct Turbo : Fast {
 struct TurboCount : Fast {
   static constexpr bool turbo = true;
   static constexpr bool count = true;
+};
+// Flight policy of HEROAM_MODE_FAST_CLOSED: a force-free particle turns rigidly about its fixed axis, so a
+// whole flight is ONE rotation (rotate_free below) instead of one orientation update per step.  Only the
+// free-flight code is instantiated with it; the integrate kernels of that mode are Turbo's.
+struct TurboClosed : Turbo {
+  static constexpr bool closed_flight = true;
 };
 // Turbo that renormalises the orientation after every 8th step only (HEROAM_MODE_FAST_RELAXED)
 struct Turbo8 : Turbo {
@@ -311,6 +319,30 @@ __device__ __forceinline__ void advance_orientation(const Consts &c, const float
     const float inv = rsqrtf(P::dot4(na, nx, ny, nz));
     q[0] = __fmul_rn(na, inv); q[1] = __fmul_rn(nx, inv); q[2] = __fmul_rn(ny, inv); q[3] = __fmul_rn(nz, inv);
   }
+}
+
+// k force-free steps at once (HEROAM_MODE_FAST_CLOSED).  One step maps q to normalize(q + W q) with
+// W = (0, w'), w' = (dt/2) w: since q + W q = (1 + W) q and 1 + W = sqrt(1 + |w'|^2) (cos t + n sin t) with
+// n = w'/|w'| and tan t = |w'|, the normalised step is the rotor (cos t, n sin t) applied from the left,
+// and k steps are the rotor (cos kt, n sin kt).  This is the exact solution of the map the reference
+// iterates; what it does not reproduce is the reference's per-step rounding, so positions agree with
+// the stepped arithmetic to the size of its own rounding walk (tests/horizon_common.py, "fast_closed").
+// Single precision suffices: |w'| ~ 1e-5, k t <= ~1e2 rad over a whole trajectory, so the angle is
+// good to ~1e-5 rad (5e-4 A on R = 47.8 A) in the worst case and to ~1e-7 rad for a typical flight.
+__device__ __forceinline__ void rotate_free(const float w[3], float q[4], uint32_t k) {
+  const float s2 = fmaf(w[2], w[2], fmaf(w[1], w[1], w[0] * w[0]));
+  if (!(s2 > 0.0f) || k == 0u) return;
+  const float s = sqrtf(s2);
+  float sn, cs;
+  sincosf(__uint2float_rn(k) * atanf(s), &sn, &cs);
+  const float g = sn / s, ax = w[0] * g, ay = w[1] * g, az = w[2] * g;
+  const float qa = q[0], qx = q[1], qy = q[2], qz = q[3];
+  const float na = fmaf(cs, qa, -fmaf(az, qz, fmaf(ay, qy, ax * qx)));
+  const float nx = fmaf(cs, qx, fmaf(-az, qy, fmaf(ay, qz, ax * qa)));
+  const float ny = fmaf(cs, qy, fmaf(az, qx, fmaf(-ax, qz, ay * qa)));
+  const float nz = fmaf(cs, qz, fmaf(az, qa, fmaf(-ay, qx, ax * qy)));
+  const float inv = rsqrtf(fmaf(nz, nz, fmaf(ny, ny, fmaf(nx, nx, na * na))));
+  q[0] = __fmul_rn(na, inv); q[1] = __fmul_rn(nx, inv); q[2] = __fmul_rn(ny, inv); q[3] = __fmul_rn(nz, inv);
 }
 
 // the renormalisation on its own (Turbo): lets a kernel that holds several particles take ONE

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <thread>
 #include <vector>
 
@@ -183,11 +184,15 @@ extern "C" int heroam_gpu_create(const heroam_config *conf, const float *force_l
   memset(&options, 0, sizeof options);
   if (opt) options = *opt;
   if (options.mode != HEROAM_MODE_EXACT && options.mode != HEROAM_MODE_FAST && options.mode != HEROAM_MODE_FAST_PLAIN &&
-      options.mode != HEROAM_MODE_FAST_RELAXED)
+      options.mode != HEROAM_MODE_FAST_RELAXED && options.mode != HEROAM_MODE_FAST_CLOSED)
     return fail(HEROAM_E_ARG, "unknown mode %d", options.mode);
   heroam_ctx *ctx = new heroam_ctx();
   ctx->device = device;
   ctx->conf = *conf;
+  // seed = 0: the reference seeds from the clock (simulation.c:283-286).  Resolved once per context; a
+  // caller driving several contexts as one run resolves it itself and passes the same seed to all
+  // (host/heroam_main.c does).
+  if (ctx->conf.seed == 0) ctx->conf.seed = (long)time(nullptr);
   ctx->opt = options;
   ctx->sm_count = prop.multiProcessorCount;
   const int rc = init_context(ctx, force_list);
@@ -278,7 +283,7 @@ extern "C" void heroam_gpu_destroy(heroam_ctx *ctx) {
 extern "C" int heroam_gpu_set_mode(heroam_ctx *ctx, int mode) {
   if (!ctx) return fail(HEROAM_E_ARG, "null context");
   if (mode != HEROAM_MODE_EXACT && mode != HEROAM_MODE_FAST && mode != HEROAM_MODE_FAST_PLAIN &&
-      mode != HEROAM_MODE_FAST_RELAXED)
+      mode != HEROAM_MODE_FAST_RELAXED && mode != HEROAM_MODE_FAST_CLOSED)
     return fail(HEROAM_E_ARG, "unknown mode %d", mode);
   ctx->opt.mode = mode;
   return HEROAM_OK;
@@ -431,16 +436,16 @@ static void update_regime(const heroam_ctx *ctx, Regime &rg) {
   rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
 }
 
-// R: arithmetic of the resolve steps, P: of the integrate kernels
-template <class R, class P>
+// P: arithmetic of the integrate kernels, F: of the free flights
+template <class P, class F>
 static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, bool draining = false) {
   const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
   if (bin >= BIN_FREE && bin < BIN_CORE) {
     const uint2 *flyers = ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride;
-    if (v.c.clock_exact) k_free_flight<P, true><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
-    else k_free_flight<P, false><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
+    if (v.c.clock_exact) k_free_flight<F, true><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
+    else k_free_flight<F, false><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
     CU(cudaGetLastError());
     return HEROAM_OK;
   }
@@ -497,8 +502,8 @@ static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, 
   return HEROAM_OK;
 }
 
-// R: arithmetic of the once-per-pass resolve kernel; H: arithmetic of the integrate kernels
-template <class R, class H>
+// R: arithmetic of the once-per-pass resolve kernel; H: arithmetic of the integrate kernels; F: of the free flights
+template <class R, class H, class F = H>
 static int run_passes(heroam_ctx *ctx, const Consts &c) {
   DevView v = make_view(ctx, c);
   if (H::turbo) {
@@ -523,7 +528,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     const Segments sg = pass_segments(ctx, rg);
     if (lists.count)
-      k_resolve_and_bin<R, H><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list,
+      k_resolve_and_bin<R, F><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, sg, cap, ctx->d_bin_count, ctx->d_bin_list,
                                                                                ctx->d_free_list, lists);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
@@ -553,7 +558,7 @@ static int run_passes(heroam_ctx *ctx, const Consts &c) {
       if (!cnt) continue;
       // the bin streams start after ev_i0, i.e. after this pass's resolve kernel
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<R, H>(ctx, v, b, cnt, rg.draining);
+      int rc = launch_bin<H, F>(ctx, v, b, cnt, rg.draining);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
@@ -597,6 +602,7 @@ extern "C" int heroam_gpu_run(heroam_ctx *ctx) {
   rc = ctx->opt.mode == HEROAM_MODE_EXACT          ? run_passes<Exact, Exact>(ctx, c)
        : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN   ? run_passes<Fast, Fast>(ctx, c)
        : ctx->opt.mode == HEROAM_MODE_FAST_RELAXED ? run_passes<Fast, Turbo8>(ctx, c)
+       : ctx->opt.mode == HEROAM_MODE_FAST_CLOSED  ? run_passes<Fast, Turbo, TurboClosed>(ctx, c)
        : ctx->opt.count_work                     ? run_passes<Fast, TurboCount>(ctx, c)
                                                  : run_passes<Fast, Turbo>(ctx, c);
   return rc;

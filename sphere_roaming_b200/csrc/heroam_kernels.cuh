@@ -511,9 +511,14 @@ __device__ inline void rewind_loners(const DevView &v, TrajMeta &m, Counters &wo
     ld3(p->ang_velocity, w_rec);
     load_w<P>(c, w_rec, w);
     float time = m.loner_time0;
-    for (uint32_t k = m.loner_from; k < m.steps; ++k) {
-      advance_orientation<P>(c, w, q, renorm_at<P>(k));
-      time = __fadd_rn(time, c.dt);
+    if (P::closed_flight) {
+      rotate_free(w, q, m.steps - m.loner_from);
+      for (uint32_t k = m.loner_from; k < m.steps; ++k) time = __fadd_rn(time, c.dt);
+    } else {
+      for (uint32_t k = m.loner_from; k < m.steps; ++k) {
+        advance_orientation<P>(c, w, q, renorm_at<P>(k));
+        time = __fadd_rn(time, c.dt);
+      }
     }
     pole_position<P>(c, q, r);
     stored_velocity<P>(r, w_rec, vel, v2);
@@ -811,6 +816,13 @@ __device__ __forceinline__ void fly_together(const Consts &c, Flyer (&fl)[N]) {
   uint32_t k = fl[0].from;
   const uint32_t until = fl[0].until;
   float time = fl[0].time;
+  if (P::closed_flight) {  // the whole flight as one rotation; only the clock still counts the steps
+#pragma unroll
+    for (int i = 0; i < N; ++i) rotate_free(fl[i].w, fl[i].q, until - k);
+    if (!CLOCK_PRODUCT)
+      for (; k < until; ++k) time = __fadd_rn(time, c.dt);
+    k = until;
+  }
   if (P::renorm_every > 1u) {
     // renormalisation after every renorm_every-th absolute step: single steps up to the next
     // boundary, then whole blocks without any test, then the remainder

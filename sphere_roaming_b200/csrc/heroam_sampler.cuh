@@ -482,7 +482,7 @@ static uint32_t pool_slot_capacity(double lambda) {
   return cap;
 }
 
-template <class R, class H>
+template <class R, class H, class F = H>
 static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in, uint32_t slots) {
   PoolParams pool = pool_in;
   pool.refill = 1;
@@ -507,7 +507,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     const Segments sg = pass_segments(ctx, rg);
     if (lists.count)
-      k_pool_resolve<R, H><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count,
+      k_pool_resolve<R, F><<<(lists.count + 127) / 128, 128, 0, ctx->main>>>(v, pool, sg, step_cap, ctx->d_bin_count,
                                                                            ctx->d_bin_list, ctx->d_free_list, lists);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
@@ -551,7 +551,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
       const uint32_t cnt = ctx->h_bin_count[b];
       if (!cnt) continue;
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<R, H>(ctx, v, b, cnt, rg.draining);
+      int rc = launch_bin<H, F>(ctx, v, b, cnt, rg.draining);
       if (rc) return rc;
       ctx->info.kernel_launches++;
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
@@ -602,6 +602,8 @@ extern "C" int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_numbe
   const uint32_t cap = pool_slot_capacity(lambda_max);
   const unsigned long long pool_max = ctx->opt.pool_slots > 0 ? (unsigned long long)ctx->opt.pool_slots : (1ull << 22);
   const uint32_t slots = (uint32_t)(count < pool_max ? count : pool_max);
+  if ((unsigned long long)slots * cap > 0xfffffff0ull)  // record offsets are 32-bit (TrajMeta::first)
+    return fail(HEROAM_E_ARG, "pool_slots = %u with %u records per slot exceeds 2^32 particle records", slots, cap);
   rc = reserve(ctx, slots, (size_t)slots * cap);
   if (rc) return rc;
   ctx->he_number = he_number;
@@ -631,6 +633,7 @@ extern "C" int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_numbe
   rc = ctx->opt.mode == HEROAM_MODE_EXACT          ? run_pool<Exact, Exact>(ctx, c, pool, slots)
        : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN   ? run_pool<Fast, Fast>(ctx, c, pool, slots)
        : ctx->opt.mode == HEROAM_MODE_FAST_RELAXED ? run_pool<Fast, Turbo8>(ctx, c, pool, slots)
+       : ctx->opt.mode == HEROAM_MODE_FAST_CLOSED  ? run_pool<Fast, Turbo, TurboClosed>(ctx, c, pool, slots)
        : ctx->opt.count_work                     ? run_pool<Fast, TurboCount>(ctx, c, pool, slots)
                                                  : run_pool<Fast, Turbo>(ctx, c, pool, slots);
   std::vector<DevStats> h((size_t)n_points);

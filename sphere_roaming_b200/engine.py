@@ -20,8 +20,10 @@ MODE_EXACT = 0
 MODE_FAST = 1
 MODE_FAST_PLAIN = 2
 MODE_FAST_RELAXED = 3
+MODE_FAST_CLOSED = 4
 _MODES = {"exact": MODE_EXACT, "fast": MODE_FAST, "fast_plain": MODE_FAST_PLAIN, "fast_relaxed": MODE_FAST_RELAXED,
-          0: MODE_EXACT, 1: MODE_FAST, 2: MODE_FAST_PLAIN, 3: MODE_FAST_RELAXED}
+          "fast_closed": MODE_FAST_CLOSED, 0: MODE_EXACT, 1: MODE_FAST, 2: MODE_FAST_PLAIN, 3: MODE_FAST_RELAXED,
+          4: MODE_FAST_CLOSED}
 
 DONE_SUCCESS, DONE_MAXTIME, DONE_DEADLOCK, DONE_STEPCAP, DONE_UNSUPPORTED = 0, 1, 2, 4, 6
 

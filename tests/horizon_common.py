@@ -32,6 +32,7 @@ HORIZON_TOLERANCE = {
     "reference_release": dict(matched=0.95, near=0.975, same_flags=0.99, pos_median=5e-3, pos_99=0.5),
     "fast": dict(matched=0.90, near=0.96, same_flags=0.99, pos_median=5e-3, pos_99=0.5),
     "fast_relaxed": dict(matched=0.70, near=0.92, same_flags=0.98, pos_median=5e-2, pos_99=2.0),
+    "fast_closed": dict(matched=0.70, near=0.92, same_flags=0.98, pos_median=5e-2, pos_99=2.0),
     # ~31 particles per trajectory on the small droplet (C4, lambda = 31.5): one flipped near-miss anywhere
     # changes the exit; measured 78 % / 91 % / 63 of 64
     "fast_dense": dict(matched=0.70, near=0.85, same_flags=0.95, pos_median=5e-3, pos_99=0.5),

@@ -67,7 +67,7 @@ def test_c2_exact_bitwise_at_1e7(need_gpu, table):
     assert (res["status"] == engine.DONE_MAXTIME).sum() > 20, "the fixture should contain trajectories that run to max_time"
 
 
-@pytest.mark.parametrize("mode", ["fast", "fast_relaxed"])
+@pytest.mark.parametrize("mode", ["fast", "fast_relaxed", "fast_closed"])
 def test_c2_fast_within_stated_tolerance_at_1e7(need_gpu, table, mode):
     g = load("c2")
     counts, init, want = g["counts"], g["init"], g["final"]
@@ -93,7 +93,7 @@ def binned_ks(sample, hist, max_time):
     return d, stats.kstwobign.sf(d * np.sqrt(n_eff))
 
 
-@pytest.mark.parametrize("mode", ["fast", "fast_relaxed"])
+@pytest.mark.parametrize("mode", ["fast", "fast_relaxed", "fast_closed"])
 def test_c2_statistics_at_1e7(need_gpu, table, mode):
     """Check (b) at the benchmark's own horizon: Philox-sampled GPU run (200 000 trajectories to
     max_time = 1e7) against the reference sample (libc-rand sampler + strict integrator, 4096

@@ -137,10 +137,11 @@ def test_large_table_gathers_from_hbm(need_gpu, port):
 POSITION_TOLERANCE = {
     "fast": (2e-4, 5e-3),          # measured 2.4e-5 / 6.0e-4: the roundings mirror the reference's step for step
     "fast_relaxed": (5e-3, 1e-1),  # measured 1.6e-3 / 2.3e-2: renormalisation every 8th step, independent rounding walk
+    "fast_closed": (5e-3, 1e-1),   # free flights as single rotations: the same class (the reference's own rounding walk)
 }
 
 
-@pytest.mark.parametrize("mode", ["fast", "fast_relaxed"])
+@pytest.mark.parametrize("mode", ["fast", "fast_relaxed", "fast_closed"])
 def test_fast_mode_within_stated_tolerance(need_gpu, port, table, mode):
     n, max_time = 4096, 2.0e5
     conf = make_config(number=n, max_time=max_time)

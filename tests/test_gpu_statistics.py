@@ -16,7 +16,7 @@ HE = 10000
 P_MIN = 1e-3
 
 
-@pytest.mark.parametrize("mode", ["fast", "fast_relaxed"])
+@pytest.mark.parametrize("mode", ["fast", "fast_relaxed", "fast_closed"])
 def test_histograms_agree_with_reference_distribution(port, table, mode):
     if engine.device_count() < 1:
         pytest.fail("needs a CUDA device")
