@@ -15,7 +15,9 @@ from sphere_roaming_b200 import engine
 from sphere_roaming_b200.forcetable import synthetic_table
 from sphere_roaming_b200.types import make_config, offsets_of
 
-table = synthetic_table()
+TLARGE = int(os.environ.get("TLARGE", 0))  # 1: the 26.6 M-entry table (106 MB), gathers leave L1/L2
+GRID, LENGTH = (6.0e-5, 26_600_000) if TLARGE else (0.001, 1_596_000)
+table = synthetic_table(length=LENGTH, grid=GRID)
 HE = int(os.environ.get("HE", 10000))
 STEPS = int(os.environ.get("STEPS", 4096))
 M = int(os.environ.get("M", 148 * 1024))
@@ -26,7 +28,7 @@ SEG = int(os.environ.get("SEG", 0))
 
 def batch_with_n(n, m):
     lam_per_intensity = 3.9337242843335494 * (HE / 10000.0)
-    conf = make_config(number=4096, intensity=max(n, 1) / lam_per_intensity, max_time=1e7)
+    conf = make_config(number=4096, intensity=max(n, 1) / lam_per_intensity, max_time=1e7, force_grid=GRID, force_grid_length=LENGTH)
     with engine.Engine(conf, table) as eng:
         counts, flat = eng.sample(HE, 4096)
     off = offsets_of(counts)
@@ -44,7 +46,7 @@ peak = None
 for n in NS:
     m = M if n <= 8 else (148 * 256 if n <= 16 else max(148 * 16, M // 32))
     counts, flat = batch_with_n(n, m)
-    conf = make_config(number=m, max_time=1e7)
+    conf = make_config(number=m, max_time=1e7, force_grid=GRID, force_grid_length=LENGTH)
     for mode in MODES:
         with engine.Engine(conf, table, mode=mode, max_steps=STEPS, segment_steps=SEG) as eng:
             if peak is None:
