@@ -413,27 +413,27 @@ def gpu_arm(args, table):
     relaxed = None
     if args.mode == "fast" and args.relaxed_step:
         eng.set_mode("fast_relaxed")
-        k_rel = max(1, min(K, args.relaxed_step))
+        k_rel = K if args.relaxed_step < 0 else max(1, min(K, args.relaxed_step))
         f, n = block(W, k_rel)
         flush.fill_(3)
         barrier()
         st = eng.run_stats(HE, n, first_index=f)
         relaxed = summarise(st["info"], inrange_ratio, "fast_relaxed")
-        relaxed["note"] = (f"HEROAM_MODE_FAST_RELAXED (opt-in): {k_rel} of the K steps as one run with the orientation renormalised "
-                           "after every 8th step; its own position tolerance (DESIGN.md section 4)")
+        relaxed["note"] = (f"HEROAM_MODE_FAST_RELAXED (opt-in): the same index block as the headline ({k_rel} steps as one run) with the "
+                           "orientation renormalised after every 8th step; its own position tolerance (DESIGN.md section 4)")
         eng.set_mode(args.mode)
 
     # ---- closed-form free flight (opt-in), for the record -------------------------------------------
     closed = None
     if args.mode == "fast" and args.closed_step:
         eng.set_mode("fast_closed")
-        k_cl = max(1, min(K, args.closed_step))
+        k_cl = K if args.closed_step < 0 else max(1, min(K, args.closed_step))
         f, n = block(W, k_cl)
         flush.fill_(3)
         barrier()
         st = eng.run_stats(HE, n, first_index=f)
         closed = summarise(st["info"], inrange_ratio, "fast_closed")
-        closed["note"] = (f"HEROAM_MODE_FAST_CLOSED (opt-in): {k_cl} of the K steps as one run with every free flight taken as one "
+        closed["note"] = (f"HEROAM_MODE_FAST_CLOSED (opt-in): the same index block as the headline ({k_cl} steps as one run) with every free flight taken as one "
                           "rotation instead of step by step; particle-steps count the steps advanced, not instructions -- "
                           "roofline_frac charges nothing for a flight step; its own tolerance row (DESIGN.md section 4)")
         eng.set_mode(args.mode)
@@ -590,13 +590,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end arm (0 = all K)")
     ap.add_argument("--warmup-e2e", type=int, default=1)
     ap.add_argument("--exact-step", type=int, default=1)
-    ap.add_argument("--relaxed-step", type=int, default=4, help="steps of the relaxed-mode run (0 = skip)")
-    ap.add_argument("--closed-step", type=int, default=4, help="steps of the closed-form-flight run (0 = skip)")
+    ap.add_argument("--relaxed-step", type=int, default=-1, help="steps of the relaxed-mode run (0 = skip, -1 = the same K steps)")
+    ap.add_argument("--closed-step", type=int, default=-1, help="steps of the closed-form-flight run (0 = skip, -1 = the same K steps)")
     ap.add_argument("--extras", type=int, default=1, help="0 = skip the c2_single_run / c3 / c4_sweep / c5_slice / t_large legs")
     ap.add_argument("--c2-number", type=int, default=1000000)
     ap.add_argument("--c3-number", type=int, default=10000)
     ap.add_argument("--c4-number", type=int, default=100000, help="trajectories per sweep point (whole job)")
-    ap.add_argument("--c5-number", type=int, default=8000000, help="trajectories of the C5 slice (whole job)")
+    ap.add_argument("--c5-number", type=int, default=6000000, help="trajectories of the C5 slice (whole job)")
     ap.add_argument("--t-large", type=int, default=262144, help="trajectories of the T-large leg (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
