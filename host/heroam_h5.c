@@ -504,6 +504,7 @@ struct heroam_h5_reader {
   long n_objects;
   unsigned long long *step_header; /* object header address of /Step_k, 0 = absent */
   size_t n_steps_cap;
+  unsigned long long file_bytes;   /* sizes and counts read from the file are checked against this */
 };
 
 static int read_at(heroam_h5_reader *r, unsigned long long addr, void *dst, size_t n) {
@@ -524,6 +525,7 @@ static int walk_header(heroam_h5_reader *r, unsigned long long addr, msg_fn fn, 
   unsigned long long cont_addr[16], cont_size[16];
   int n_cont = 0, at_cont = 0;
   for (;;) {
+    if (block_size > r->file_bytes) return h5fail("header block of %llu bytes in a file of %llu", block_size, r->file_bytes);
     unsigned char *blk = (unsigned char *)malloc(block_size ? block_size : 1);
     if (!blk) return h5fail("out of memory");
     if (read_at(r, block_addr, blk, block_size)) { free(blk); return -1; }
@@ -624,6 +626,8 @@ static int index_step(void *user, const char *name, unsigned long long header) {
   unsigned step;
   char tail;
   if (sscanf(name, "Step_%u%c", &step, &tail) != 1) return 0; /* not one of ours: counted, not indexed */
+  /* every group costs well over 64 bytes of file: a step number beyond that is not from a writer of this format */
+  if ((unsigned long long)step > r->file_bytes / 64u) return h5fail("group %s in a file of %llu bytes", name, r->file_bytes);
   if (step >= r->n_steps_cap) {
     size_t cap = r->n_steps_cap ? r->n_steps_cap : 1024;
     while (cap <= step) cap *= 2;
@@ -649,6 +653,7 @@ heroam_h5_reader *heroam_h5_open(const char *filename) {
     return NULL;
   }
   r->f = f;
+  if (fseek(f, 0, SEEK_END) == 0 && ftell(f) > 0) r->file_bytes = (unsigned long long)ftell(f);
   static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', 0x0d, 0x0a, 0x1a, 0x0a};
   unsigned char sb[SUPERBLOCK_BYTES + 8];
   unsigned long long at = 0;

@@ -111,7 +111,7 @@ static int simulate_for_number(int helium_number, const heroam_config *conf, con
   }
   char path[96];
   snprintf(path, sizeof path, "./results/particlefile_%d", helium_number);
-  if (!failed && heroam_write_particlefile(path, all, number)) {
+  if (!failed && !heroam_write_particlefile(path, all, number)) {
     perror(path);
     failed = 1;
   }
@@ -132,7 +132,7 @@ static int simulate_for_number(int helium_number, const heroam_config *conf, con
     }
   }
   snprintf(path, sizeof path, "./results/particlefile_after_%d", helium_number);
-  if (!failed && heroam_write_particlefile(path, all, number)) {
+  if (!failed && !heroam_write_particlefile(path, all, number)) {
     perror(path);
     failed = 1;
   }
@@ -202,7 +202,7 @@ int main(int argc, char *argv[]) {
   }
   struct stat st;
   if (stat("./results", &st) == -1) mkdir("./results", 0700);
-  if (heroam_write_forcelist("./results/forcelist.txt", &conf, table, count)) {
+  if (!heroam_write_forcelist("./results/forcelist.txt", &conf, table, count)) {
     perror("./results/forcelist.txt");
     free(table);
     return 1;

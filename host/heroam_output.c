@@ -15,6 +15,6 @@ int heroam_write_particlefile(const char *path, const heroam_particles *all, int
   if (!f) return 0;
   fprintf(f, "Index\tNumber\tSuccess\tTime\tX\tY\tZ\tVX\tVY\tVZ\tFX\tFY\tFZ\n"); /* main.c:65-69 */
   for (int i = 0; i < number; ++i) heroam_save_particles(f, all + i);
-  fclose(f);
-  return 1;
+  const int bad = ferror(f);
+  return fclose(f) == 0 && !bad; /* 1 = written in full (a full disk shows up here) */
 }

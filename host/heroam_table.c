@@ -16,7 +16,8 @@ void heroam_synthetic_table(float *table, long length, double start, double grid
 
 long heroam_load_force_file(const char *filename, float *table, long length) {
   memset(table, 0, (size_t)length * sizeof(float));
-  if (strncmp(filename, "synthetic", 9) == 0) {
+  if (strncmp(filename, "synthetic", 9) == 0) { /* not a file: said out loud, the reference would try to open it */
+    fprintf(stderr, "force_file = %s: using the built-in synthetic T-ref table (%ld entries), not a file\n", filename, length);
     heroam_synthetic_table(table, length, 4.0, 0.001, 1.0e-6, 2);
     return length;
   }
@@ -37,6 +38,6 @@ int heroam_write_forcelist(const char *path, const heroam_config *conf, const fl
   fprintf(f, "Distance_Squared\tForce\n");
   for (int i = 0; i < count; ++i) /* float arithmetic, int index: as main.c:151-152 */
     fprintf(f, "%f\t%.10e\n", conf->force_grid_start + conf->force_grid * i, table[i]);
-  fclose(f);
-  return 1;
+  const int bad = ferror(f);
+  return fclose(f) == 0 && !bad;
 }
