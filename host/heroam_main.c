@@ -16,6 +16,8 @@
  *   HEROAM_MODE=exact|fast   arithmetic mode (default exact)
  *   HEROAM_GPUS=n            number of GPUs to use (default: all visible)
  *   HEROAM_STATS=1           histogram-only run through heroam_gpu_run_stats (no TSV files)
+ *   HEROAM_STREAM_ABOVE=n    runs of more than n trajectories (default 2^21) write their result files block by
+ *                            block from flat buffers instead of holding every trajectory to the end
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -92,10 +94,16 @@ static int simulate_traced_block(heroam_ctx *ctx, int helium_number, heroam_part
   return failed;
 }
 
+#define STREAM_ABOVE (1 << 21)
+#define STREAM_BLOCK (1 << 20)
+static int stream_for_number(int helium_number, const heroam_config *conf, heroam_ctx **ctx, int n_gpus);
+
 static int simulate_for_number(int helium_number, const heroam_config *conf, const float *table,
                                heroam_ctx **ctx, int n_gpus) {
   (void)table; /* already resident on every GPU */
   const int number = conf->number;
+  const char *stream = getenv("HEROAM_STREAM_ABOVE"); /* tests lower the threshold */
+  if (!conf->saveflag && number > (stream ? atoi(stream) : STREAM_ABOVE)) return stream_for_number(helium_number, conf, ctx, n_gpus);
   heroam_particles *all = (heroam_particles *)calloc((size_t)(number > 0 ? number : 1), sizeof *all);
   if (!all) return 1;
   int failed = 0;
@@ -138,6 +146,89 @@ static int simulate_for_number(int helium_number, const heroam_config *conf, con
   }
   for (int i = 0; i < number; ++i) heroam_gpu_free_particles(all + i);
   free(all);
+  return failed;
+}
+
+/* Large runs (number > STREAM_ABOVE, no per-step files): the same two result files, written in trajectory order
+ * from flat page-sized blocks instead of holding `number` separately malloc'ed arrays to the end (main.c:55,
+ * simulation.c:310).  Each GPU takes STREAM_BLOCK consecutive trajectories of a round, samples them
+ * (heroam_gpu_sample_flat), keeps a copy of the initial records, integrates them (heroam_gpu_simulate_flat); the
+ * rows of the round then go to particlefile_<N> and particlefile_after_<N>.  Memory: 2 x STREAM_BLOCK x ~4 records
+ * per GPU, whatever `number` is. */
+static void write_rows(FILE *f, long first_traj, const uint32_t *counts, const heroam_particle *flat, long n) {
+  long at = 0;
+  for (long i = 0; i < n; ++i) {
+    heroam_particles one;
+    one.no = counts[i];
+    one.index = (uint32_t)(first_traj + i);
+    one.particle = (heroam_particle *)(flat + at);
+    heroam_save_particles(f, &one);
+    at += counts[i];
+  }
+}
+
+static int stream_for_number(int helium_number, const heroam_config *conf, heroam_ctx **ctx, int n_gpus) {
+  const long number = conf->number;
+  const long cap = (long)STREAM_BLOCK * 6 + 4096; /* records per block: mean 4 per trajectory at the repository's lambda */
+  char path[96];
+  snprintf(path, sizeof path, "./results/particlefile_%d", helium_number);
+  FILE *before = fopen(path, "w");
+  snprintf(path, sizeof path, "./results/particlefile_after_%d", helium_number);
+  FILE *after = fopen(path, "w");
+  uint32_t **counts = (uint32_t **)calloc((size_t)n_gpus, sizeof *counts);
+  heroam_particle **init = (heroam_particle **)calloc((size_t)n_gpus, sizeof *init);
+  heroam_particle **fin = (heroam_particle **)calloc((size_t)n_gpus, sizeof *fin);
+  long *got = (long *)calloc((size_t)n_gpus, sizeof *got);
+  int failed = !before || !after || !counts || !init || !fin || !got;
+  for (int g = 0; g < n_gpus && !failed; ++g) {
+    counts[g] = (uint32_t *)malloc((size_t)STREAM_BLOCK * sizeof(uint32_t));
+    init[g] = (heroam_particle *)malloc((size_t)cap * sizeof(heroam_particle));
+    fin[g] = (heroam_particle *)malloc((size_t)cap * sizeof(heroam_particle));
+    failed = !counts[g] || !init[g] || !fin[g];
+  }
+  if (failed) fprintf(stderr, "cannot open the result files or allocate the streaming blocks\n");
+  static const char *header = "Index\tNumber\tSuccess\tTime\tX\tY\tZ\tVX\tVY\tVZ\tFX\tFY\tFZ\n"; /* main.c:65-69 */
+  if (!failed) { fputs(header, before); fputs(header, after); }
+  for (long round0 = 0; round0 < number && !failed; round0 += (long)n_gpus * STREAM_BLOCK) {
+#pragma omp parallel for num_threads(n_gpus) schedule(static, 1) reduction(| : failed)
+    for (int g = 0; g < n_gpus; ++g) {
+      const long first = round0 + (long)g * STREAM_BLOCK;
+      long n = number - first;
+      if (n > STREAM_BLOCK) n = STREAM_BLOCK;
+      got[g] = 0;
+      if (n <= 0) continue;
+      long total = 0;
+      if (heroam_gpu_sample_flat(ctx[g], (unsigned long long)helium_number, (unsigned long long)first, (int)n, counts[g],
+                                 init[g], cap, &total) || total > cap) {
+        fprintf(stderr, "GPU %d: %s\n", g, total > cap ? "a block needs more records than reserved" : heroam_gpu_last_error());
+        failed |= 1;
+        continue;
+      }
+      memcpy(fin[g], init[g], (size_t)total * sizeof(heroam_particle));
+      if (heroam_gpu_simulate_flat(ctx[g], (unsigned long long)helium_number, counts[g], fin[g], (int)n, NULL)) {
+        fprintf(stderr, "GPU %d: %s\n", g, heroam_gpu_last_error());
+        failed |= 1;
+        continue;
+      }
+      got[g] = n;
+    }
+    for (int g = 0; g < n_gpus && !failed; ++g) {
+      write_rows(before, round0 + (long)g * STREAM_BLOCK, counts[g], init[g], got[g]);
+      write_rows(after, round0 + (long)g * STREAM_BLOCK, counts[g], fin[g], got[g]);
+    }
+    if (!failed && (ferror(before) || ferror(after))) {
+      perror("./results/particlefile");
+      failed = 1;
+    }
+  }
+  if (before && fclose(before)) failed = 1;
+  if (after && fclose(after)) failed = 1;
+  for (int g = 0; g < n_gpus; ++g) {
+    if (counts) free(counts[g]);
+    if (init) free(init[g]);
+    if (fin) free(fin[g]);
+  }
+  free(counts); free(init); free(fin); free(got);
   return failed;
 }
 

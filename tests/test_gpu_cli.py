@@ -41,6 +41,14 @@ def test_heroam_cli_writes_reference_files(tmp_path, port, table):
     assert (tmp_path / "results" / "particlefile_after_10000").read_text() == (tmp_path / "want_after").read_text()
     before = parse_particlefile(tmp_path / "results" / "particlefile_10000")
     assert len(before) == counts.sum() and np.all(before[:, 3] == 0)
+    # the streaming writer (runs above 2^21 trajectories; forced here): the same two files, byte for byte
+    for name in ("particlefile_10000", "particlefile_after_10000"):
+        os.rename(tmp_path / "results" / name, tmp_path / ("held_" + name))
+    r = subprocess.run([exe, "run.conf"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, HEROAM_STREAM_ABOVE="8"))
+    assert r.returncode == 0, r.stderr
+    for name in ("particlefile_10000", "particlefile_after_10000"):
+        assert (tmp_path / "results" / name).read_bytes() == (tmp_path / ("held_" + name)).read_bytes(), name
     # histogram-only mode
     r = subprocess.run([exe, "run.conf"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
                        env=dict(os.environ, HEROAM_STATS="1", HEROAM_MODE="fast"))
