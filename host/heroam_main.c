@@ -270,6 +270,66 @@ static int stats_for_number(int helium_number, const heroam_config *conf, heroam
   return failed;
 }
 
+/* The droplet-size sweep of main.c:158-164 in histogram mode: ONE pool run per GPU for all sizes
+ * (heroam_gpu_run_size_sweep), every size sharded by trajectory index over the GPUs. */
+static int stats_for_sweep(const heroam_config *conf, heroam_ctx **ctx, int n_gpus) {
+  int n_sizes = 0;
+  for (int n = conf->start; n < conf->stop; n += conf->step) ++n_sizes;
+  if (n_sizes < 1) return 0;
+  if (n_sizes > 32 || conf->step <= 0) return -1; /* the caller falls back to the loop of runs */
+  heroam_stats *st = (heroam_stats *)calloc((size_t)n_gpus * (size_t)n_sizes, sizeof *st);
+  heroam_size_point *pts = (heroam_size_point *)calloc((size_t)n_gpus * (size_t)n_sizes, sizeof *pts);
+  if (!st || !pts) { free(st); free(pts); return 1; }
+  int failed = 0;
+#pragma omp parallel for num_threads(n_gpus) schedule(static, 1) reduction(| : failed)
+  for (int g = 0; g < n_gpus; ++g) {
+    heroam_size_point *mine = pts + (size_t)g * n_sizes;
+    for (int i = 0; i < n_sizes; ++i) {
+      const long first = (long)g * conf->number / n_gpus, last = (long)(g + 1) * conf->number / n_gpus;
+      mine[i].he_number = (unsigned long long)(conf->start + i * conf->step);
+      mine[i].first_index = (unsigned long long)first;
+      mine[i].count = (unsigned long long)(last - first);
+    }
+    if (heroam_gpu_run_size_sweep(ctx[g], n_sizes, mine, st + (size_t)g * n_sizes)) {
+      fprintf(stderr, "GPU %d: %s\n", g, heroam_gpu_last_error());
+      failed |= 1;
+    }
+  }
+  for (int i = 0; i < n_sizes && !failed; ++i) {
+    char path[96];
+    const int helium_number = conf->start + i * conf->step;
+    snprintf(path, sizeof path, "./results/histograms_%d.tsv", helium_number);
+    FILE *f = fopen(path, "w");
+    if (!f) { perror(path); failed = 1; break; }
+    fprintf(f, "Bin\tTrajectoryExitTime\tParticleMeetingTime\n");
+    unsigned long long traj = 0;
+    for (int b = 0; b < HEROAM_HIST_T; ++b) {
+      unsigned long long a = 0, m = 0;
+      for (int g = 0; g < n_gpus; ++g) {
+        a += st[(size_t)g * n_sizes + i].hist_traj_time[b];
+        m += st[(size_t)g * n_sizes + i].hist_meet_time[b];
+      }
+      fprintf(f, "%d\t%llu\t%llu\n", b, a, m);
+    }
+    if (fclose(f)) failed = 1;
+    for (int g = 0; g < n_gpus; ++g) traj += st[(size_t)g * n_sizes + i].trajectories;
+    printf("N=%d: %llu trajectories\n", helium_number, traj);
+  }
+  if (!failed) {
+    unsigned long long psteps = 0;
+    double ms = 0;
+    for (int g = 0; g < n_gpus; ++g) {
+      psteps += st[(size_t)g * n_sizes].info.particle_steps;
+      if (st[(size_t)g * n_sizes].info.device_ms > ms) ms = st[(size_t)g * n_sizes].info.device_ms;
+    }
+    printf("%d droplet sizes as one run: %llu particle-steps in %.1f ms on %d GPU(s): %.3e particle-steps/s\n", n_sizes, psteps,
+           ms, n_gpus, psteps / (ms * 1e-3));
+  }
+  free(st);
+  free(pts);
+  return failed;
+}
+
 int main(int argc, char *argv[]) {
   if (argc < 2) {
     fprintf(stderr, "Usage: %s <config_file>\n", argv[0]);
@@ -325,8 +385,11 @@ int main(int argc, char *argv[]) {
     }
   const int stats_only = getenv("HEROAM_STATS") && atoi(getenv("HEROAM_STATS")) != 0;
   int failed = 0;
-  /* droplet-size sweep exactly as main.c:158-164 */
-  if (conf.start) {
+  /* droplet-size sweep exactly as main.c:158-164; in histogram mode all sizes share one pool run */
+  int swept = conf.start && stats_only ? stats_for_sweep(&conf, ctx, n_gpus) : -1;
+  if (swept >= 0) {
+    failed = swept;
+  } else if (conf.start) {
     for (int n = conf.start; n < conf.stop && !failed; n += conf.step)
       failed = stats_only ? stats_for_number(n, &conf, ctx, n_gpus) : simulate_for_number(n, &conf, table, ctx, n_gpus);
   } else {

@@ -142,7 +142,9 @@ typedef struct heroam_stats {
   unsigned long long hist_meet_time[HEROAM_HIST_T]; /* per frozen particle: its time        */
   unsigned long long done[8];                 /* trajectories by HEROAM_DONE_* code        */
   unsigned long long unmet_particles;         /* particles still unpaired at exit          */
-  double sum_traj_time;                       /* sum of loop times at exit [fs]            */
+  double sum_traj_time;                       /* sum of loop times at exit [fs], accumulated on the
+                                                 device as an integer count of 2^-10 fs: the same
+                                                 bits on every run                            */
   heroam_run_info info;
 } heroam_stats;
 
@@ -232,8 +234,8 @@ int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number,
  * pulse_width replaced (they only enter the mean excitation number, simulation.c:289-293) and
  * the Philox indices [first_index, first_index + count): out[p] is exactly what
  * heroam_gpu_run_stats would return for that point alone, except out[p].info, which describes
- * the whole sweep.  At most 32 points per call.  (The reference's own sweep, over droplet
- * sizes, main.c:158-164, changes the sphere radius and stays a loop of runs.) */
+ * the whole sweep.  At most 32 points per call.  (The reference's own sweep is over droplet
+ * sizes, main.c:158-164: heroam_gpu_run_size_sweep below.) */
 typedef struct heroam_sweep_point {
   float intensity;                /* [GW/cm^2] */
   float pulse_width;              /* [fs]      */
@@ -242,6 +244,21 @@ typedef struct heroam_sweep_point {
 } heroam_sweep_point;
 int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_number, int n_points,
                          const heroam_sweep_point *points, heroam_stats *out /* [n_points] */);
+
+/* The reference's own sweep -- over droplet sizes, main.c:158-164: `for (N = start; N < stop; N += step)
+ * simulate_for_number(N, ...)` -- as ONE run of the streaming pool.  Every size has its own sphere radius
+ * (simulation.c:297, :448), so the pool is partitioned: each size owns an equal share of the slots, its own
+ * constants and its own scaled copy of the force table, and all sizes share the passes -- one latency-bound
+ * end of run for the whole sweep instead of one per size.  out[p] is exactly what heroam_gpu_run_stats would
+ * return for size p alone (same Philox indices), except out[p].info, which describes the whole sweep.
+ * At most 32 sizes per call. */
+typedef struct heroam_size_point {
+  unsigned long long he_number;   /* helium atoms in the droplet */
+  unsigned long long first_index; /* first Philox trajectory index of this size (sharding) */
+  unsigned long long count;       /* trajectories of this size on this GPU */
+} heroam_size_point;
+int heroam_gpu_run_size_sweep(heroam_ctx *ctx, int n_points, const heroam_size_point *points,
+                              heroam_stats *out /* [n_points] */);
 
 int heroam_gpu_last_run_info(const heroam_ctx *ctx, heroam_run_info *out);
 

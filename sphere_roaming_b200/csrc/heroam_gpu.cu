@@ -237,9 +237,9 @@ static int init_context(heroam_ctx *ctx, const float *force_list) {
   ctx->nbr_cap = 64ull << 20;
   CU(cudaMalloc(&ctx->d_nbr_pool, ctx->nbr_cap));
   CU(cudaMalloc(&ctx->d_nbr_used, sizeof(unsigned long long)));
-  CU(cudaMalloc(&ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t)));
+  CU(cudaMalloc(&ctx->d_bin_count, (size_t)MAX_PARTS * N_BIN_COUNTERS * sizeof(uint32_t)));
   CU(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
-  CU(cudaMallocHost(&ctx->h_bin_count, N_BIN_COUNTERS * sizeof(uint32_t)));
+  CU(cudaMallocHost(&ctx->h_bin_count, (size_t)MAX_PARTS * N_BIN_COUNTERS * sizeof(uint32_t)));
   CU(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
   return HEROAM_OK;
 }
@@ -429,21 +429,22 @@ static Segments pass_segments(const heroam_ctx *ctx, const Regime &rg) {
 
 // Decide the regime of the next pass from the populations the resolve kernel just reported: fewer
 // trajectories in the full kernels than fill the GPU once means latency-bound from here on.
-static void update_regime(const heroam_ctx *ctx, Regime &rg) {
+static void update_regime(const heroam_ctx *ctx, Regime &rg, const uint64_t *bin_total = nullptr) {
   uint64_t in_kernels = 0;
   for (int b = 1; b < N_BINS; ++b)
-    if (b < BIN_FREE || b >= BIN_CORE) in_kernels += ctx->h_bin_count[b];
+    if (b < BIN_FREE || b >= BIN_CORE) in_kernels += bin_total ? bin_total[b] : ctx->h_bin_count[b];
   rg.draining = in_kernels < (uint64_t)ctx->sm_count * 768;
 }
 
 // P: arithmetic of the integrate kernels, F: of the free flights
 template <class P, class F>
-static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, bool draining = false) {
-  const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj;
+static int launch_bin(heroam_ctx *ctx, const DevView &v, int bin, uint32_t cnt, bool draining = false,
+                      uint32_t list_offset = 0, uint32_t free_offset = 0) {
+  const uint32_t *list = ctx->d_bin_list + (size_t)bin * ctx->n_traj + list_offset;
   cudaStream_t s = ctx->bin_stream[bin];
   const unsigned grid = (cnt + INTEGRATE_TPB - 1) / INTEGRATE_TPB;
   if (bin >= BIN_FREE && bin < BIN_CORE) {
-    const uint2 *flyers = ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride;
+    const uint2 *flyers = ctx->d_free_list + (size_t)(bin - BIN_FREE) * ctx->free_stride + free_offset;
     if (v.c.clock_exact) k_free_flight<F, true><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
     else k_free_flight<F, false><<<(cnt + 127) / 128, 128, 0, s>>>(v, flyers, cnt);
     CU(cudaGetLastError());

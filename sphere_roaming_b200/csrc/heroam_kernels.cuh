@@ -37,7 +37,9 @@ constexpr int BIN_CORE = BIN_FREE + N_FREE_TIERS;  // BIN_CORE + a: cores of spl
 constexpr int N_BINS = BIN_CORE + 9;
 constexpr int LIVE_SLOT = N_BINS;         // bin_count[LIVE_SLOT]: live trajectories seen by the resolve kernel
 constexpr int LAG_SLOT = N_BINS + 1;      // bin_count[LAG_SLOT]: 0xffffffff - (fewest steps done by a live trajectory)
-constexpr int N_BIN_COUNTERS = N_BINS + 2;
+constexpr int PART_LIVE_SLOT = N_BINS + 2; // bin_count[PART_LIVE_SLOT]: live trajectories of this part of a partitioned pool
+constexpr int N_BIN_COUNTERS = N_BINS + 3;
+constexpr int MAX_PARTS = 32;              // parts of a partitioned pool (a droplet-size sweep as one run)
 constexpr int FREE_MAX_A = 8;     // the free-flight analysis is done for trajectories with <= 8 moving particles
 constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
 constexpr int INTEGRATE_TPB = 128;
@@ -673,35 +675,51 @@ __device__ inline Schedule schedule_segment(const DevView &v, TrajMeta &m, const
 // Append what a resolve thread scheduled.  Integrate bins: warp-aggregated, one atomic per
 // (warp, bin); must be called by all 32 lanes.  Flyers: one entry per PARTICLE, (trajectory,
 // slot in its act list).
-__device__ inline void append_schedule(const Schedule &sc, uint32_t t, uint32_t stride, uint32_t *__restrict__ bin_count,
+// Where a resolve thread puts what it scheduled.  An ordinary run is one part: its counters are the pass's
+// counters and its lists start at the beginning of every bin's list.  A partitioned pool (a droplet-size sweep as
+// one run: every size has its own sphere radius, hence its own constants and its own scaled table) gives each
+// part its own bin counters and its own stretch of every list, so that each (part, bin) is launched with the
+// part's constants in the constant bank.
+struct PartSlice {
+  uint32_t *bin_count;     // this part's counters (N_BIN_COUNTERS of them)
+  uint32_t *global_count;  // the counters of part 0: LIVE_SLOT (cursor of the live list) and LAG_SLOT are per pass
+  uint32_t part;           // key for the warp-level aggregation: lanes of different parts never share an atomic
+  uint32_t list_offset;    // start of this part inside every bin's list
+  uint32_t free_offset;    // start of this part inside every free-flight tier's list
+};
+
+__device__ inline void append_schedule(const Schedule &sc, uint32_t t, uint32_t stride, const PartSlice &ps,
                                        uint32_t *__restrict__ bin_list, uint2 *__restrict__ free_list,
                                        uint32_t free_stride, uint32_t *__restrict__ live_out, uint32_t steps_done) {
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned peers = __match_any_sync(0xffffffffu, sc.bin);
+  const unsigned peers = __match_any_sync(0xffffffffu, sc.bin >= 0 ? (int)(ps.part * 64u) + sc.bin : -1);
   {  // live trajectories (anything scheduled): counted and listed for the next pass, one atomic per warp
     const bool is_live = sc.bin >= 0 || sc.fly_tier >= 0;
     const unsigned alive = __ballot_sync(0xffffffffu, is_live);
     if (alive) {
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(bin_count + LIVE_SLOT, (uint32_t)__popc(alive));
+      if (lane == 0) base = atomicAdd(ps.global_count + LIVE_SLOT, (uint32_t)__popc(alive));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (is_live) live_out[base + __popc(alive & ((1u << lane) - 1u))] = t;
       // the trajectory furthest behind: the longest chain of steps still to come bounds the end of the run
       const uint32_t lag = __reduce_max_sync(0xffffffffu, is_live ? 0xffffffffu - steps_done : 0u);
-      if (lane == 0) atomicMax(bin_count + LAG_SLOT, lag);
+      if (lane == 0) atomicMax(ps.global_count + LAG_SLOT, lag);
+      // live trajectories per part (its free slots staying free tells the host that the part's index space is used up)
+      const unsigned same_part = __match_any_sync(0xffffffffu, is_live ? (int)ps.part : -1);
+      if (is_live && (int)lane == __ffs(same_part) - 1) atomicAdd(ps.bin_count + PART_LIVE_SLOT, (uint32_t)__popc(same_part));
     }
   }
   if (sc.bin >= 0) {
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(bin_count + sc.bin, (uint32_t)__popc(peers));
+    if ((int)lane == leader) base = atomicAdd(ps.bin_count + sc.bin, (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    bin_list[(size_t)sc.bin * stride + base + rank] = t;
+    bin_list[(size_t)sc.bin * stride + ps.list_offset + base + rank] = t;
   }
   if (sc.fly_tier >= 0 && sc.fly_count) {
-    const uint32_t base = atomicAdd(bin_count + BIN_FREE + sc.fly_tier, sc.fly_count);
-    uint2 *list = free_list + (size_t)sc.fly_tier * free_stride;
+    const uint32_t base = atomicAdd(ps.bin_count + BIN_FREE + sc.fly_tier, sc.fly_count);
+    uint2 *list = free_list + (size_t)sc.fly_tier * free_stride + ps.free_offset;
     for (uint32_t s = 0; s < sc.fly_count; ++s) list[base + s] = make_uint2(t, sc.fly_first + s);
   }
 }
@@ -774,7 +792,8 @@ __global__ void k_resolve_and_bin(DevView v, Segments sg, uint32_t step_cap, uin
       steps_done = m.steps;
     }
   }
-  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride, live.out, steps_done);
+  const PartSlice whole = {bin_count, bin_count, 0u, 0u, 0u};
+  append_schedule(sc, t, v.n_traj, whole, bin_list, free_list, sg.free_stride, live.out, steps_done);
   flush_work(v, work);
 }
 

@@ -235,7 +235,9 @@ struct DevStats {
   unsigned long long unmet_particles;
   unsigned long long particles;
   unsigned long long trajectories;
-  double sum_traj_time;
+  unsigned long long sum_traj_time_q10;  // sum of the loop times at exit in units of 2^-10 fs: integer, so that the sum
+                                         // does not depend on the order in which the atomics land (a double sum did,
+                                         // in its last bits, from run to run)
 };
 
 __device__ __forceinline__ int time_bin(float t, float max_time) {
@@ -248,7 +250,7 @@ __device__ inline void accumulate_stats(const DevView &v, const TrajMeta &m, Dev
   atomicAdd(&st->hist_traj_time[time_bin(m.time, v.c.max_time)], 1ull);
   const uint32_t code = m.status >= ST_DONE ? m.status - ST_DONE : 7u;
   atomicAdd(&st->done[code < 8u ? code : 7u], 1ull);
-  atomicAdd(&st->sum_traj_time, (double)m.time);
+  atomicAdd(&st->sum_traj_time_q10, (unsigned long long)__float2ll_rn(m.time * 1024.0f));
   unsigned long long unmet = 0;
   for (uint32_t j = 0; j < m.no; ++j) {
     const heroam_particle *p = v.particles + m.first + j;
@@ -286,6 +288,19 @@ constexpr uint32_t ST_FREE = 0xfffffff0u;
 // own histogram block.
 constexpr int MAX_SWEEP_POINTS = 32;
 
+// One part of a partitioned pool: a droplet size of a size sweep (reference main.c:158-164) run as one pool run.
+// The slots are divided evenly among the parts, slot t belongs to part t / slots_per_part and only ever holds
+// that part's trajectories, so a (part, bin) list can be launched with the part's constants.
+struct PartParams {
+  Consts c;                       // radius, scales ... of this droplet size
+  const float *table_k;           // the table scaled by this part's kappa (Turbo)
+  unsigned long long he_number;   // Philox key / lambda of this size
+  unsigned long long first_index; // first Philox trajectory index of this part (sharding)
+  unsigned long long count;       // trajectories of this part on this GPU
+  double limit;                   // exp(-lambda)
+  double radius_init;             // 2.22 * pow(N, 1/3) in double (simulation.c:297)
+};
+
 struct PoolParams {
   SampleParams sp;              // sp.limit / sp.first_index are per point, see below
   unsigned long long *cursor;   // next position in the concatenated index space
@@ -293,7 +308,11 @@ struct PoolParams {
   uint32_t cap;                 // records per slot
   uint32_t n_points;
   DevStats *stats;              // n_points blocks
-  uint32_t refill;              // 0: the index space is used up (the host has seen free slots stay free)
+  uint32_t refill;              // bit p = 0: the index space of part p is used up (the host has seen free slots stay
+                                // free); an ordinary run is part 0
+  uint32_t n_parts;             // > 1: partitioned pool, `parts` and `slots_per_part` apply, `cursor` is an array
+  uint32_t slots_per_part;
+  const PartParams *parts;      // device memory
   unsigned long long point_end[MAX_SWEEP_POINTS];    // exclusive end of each point in the index space
   unsigned long long point_first[MAX_SWEEP_POINTS];  // its first Philox trajectory index
   double point_limit[MAX_SWEEP_POINTS];              // its exp(-lambda)
@@ -320,8 +339,27 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
   Counters work = {};
   Schedule sc;
   uint32_t steps_done = 0;
+  PartSlice ps = {bin_count, bin_count, 0u, 0u, 0u};
   if (idx < live.count) {
     if (live.in) t = live.in[idx];
+    // a partitioned pool: this slot's part decides constants, sampling parameters, counters and list stretches
+    SampleParams sp = pool.sp;
+    unsigned long long *cursor = pool.cursor;
+    unsigned long long part_count = pool.count;
+    if (pool.n_parts > 1u) {
+      const uint32_t part = t / pool.slots_per_part;
+      const PartParams &pp = pool.parts[part];
+      v.c = pp.c;
+      v.table_k = pp.table_k;
+      sp.he_number = pp.he_number;
+      sp.radius_init = pp.radius_init;
+      cursor = pool.cursor + part;
+      part_count = pp.count;
+      ps.bin_count = bin_count + part * N_BIN_COUNTERS;
+      ps.part = part;
+      ps.list_offset = part * pool.slots_per_part;
+      ps.free_offset = part * pool.slots_per_part * pool.cap;
+    }
     TrajMeta m = v.meta[t];
     // a freshly spawned trajectory can be over at once (nobody moving), hence the loop
     for (;;) {
@@ -337,16 +375,25 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
       // (millions, late in a run) would otherwise all serialise on the cursor's atomic in every pass,
       // ~1 ns each -- 4 ms per pass with 4e6 free slots.  The cursor only grows, so a stale value
       // can only send a thread on to the atomic, never past a trajectory.
-      if (!pool.refill) break;
-      if (*reinterpret_cast<volatile unsigned long long *>(pool.cursor) >= pool.count) break;
-      const unsigned long long idx = atomicAdd(pool.cursor, 1ull);
-      if (idx >= pool.count) break;
+      if (!((pool.refill >> ps.part) & 1u)) break;
+      if (*reinterpret_cast<volatile unsigned long long *>(cursor) >= part_count) break;
+      const unsigned long long idx_claimed = atomicAdd(cursor, 1ull);
+      if (idx_claimed >= part_count) break;
       uint32_t pt = 0;
-      while (pt + 1u < pool.n_points && idx >= pool.point_end[pt]) ++pt;
-      const unsigned long long local = idx - (pt ? pool.point_end[pt - 1u] : 0ull);
+      unsigned long long stream_index;
+      double limit;
+      if (pool.n_parts > 1u) {
+        pt = ps.part;
+        stream_index = pool.parts[pt].first_index + idx_claimed;
+        limit = pool.parts[pt].limit;
+      } else {
+        while (pt + 1u < pool.n_points && idx_claimed >= pool.point_end[pt]) ++pt;
+        stream_index = pool.point_first[pt] + (idx_claimed - (pt ? pool.point_end[pt - 1u] : 0ull));
+        limit = pool.point_limit[pt];
+      }
       Philox g;
-      g.begin(pool.sp.seed, pool.sp.he_number, pool.point_first[pt] + local);
-      const uint32_t n = sample_count(g, pool.point_limit[pt]);
+      g.begin(sp.seed, sp.he_number, stream_index);
+      const uint32_t n = sample_count(g, limit);
       m.point = pt;
       m.no = n; m.steps = 0; m.time = 0.0f; m.n_flagged = 0; m.step_stop = 0;
       m.n_loners = 0; m.loner_from = 0; m.loner_until = 0; m.loner_time0 = 0.0f; m.cross_from = 0; m.core_slots = 0;
@@ -357,7 +404,7 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
         continue;
       }
       heroam_particle *p = v.particles + m.first;
-      sample_trajectory(g, pool.sp, v.c, v.table, p, n);
+      sample_trajectory(g, sp, v.c, v.table, p, n);
       for (uint32_t j = 0; j < n; ++j) m.n_flagged += p[j].success ? 1u : 0u;
       m.n_active = n - m.n_flagged;
       m.core_slots = m.n_active;
@@ -366,7 +413,7 @@ __global__ void k_pool_resolve(DevView v, PoolParams pool, Segments sg, uint32_t
     v.meta[t] = m;
     steps_done = m.steps;
   }
-  append_schedule(sc, t, v.n_traj, bin_count, bin_list, free_list, sg.free_stride, live.out, steps_done);
+  append_schedule(sc, t, v.n_traj, ps, bin_list, free_list, sg.free_stride, live.out, steps_done);
   flush_work(v, work);
 }
 
@@ -482,19 +529,26 @@ static uint32_t pool_slot_capacity(double lambda) {
   return cap;
 }
 
+// host copy of the parts of a partitioned pool (empty for an ordinary run)
+struct PoolParts {
+  std::vector<PartParams> host;
+};
+
 template <class R, class H, class F = H>
-static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in, uint32_t slots) {
+static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in, uint32_t slots, const PoolParts &parts) {
   PoolParams pool = pool_in;
-  pool.refill = 1;
+  const uint32_t n_parts = pool.n_parts > 1u ? pool.n_parts : 1u;
+  pool.refill = n_parts >= 32u ? 0xffffffffu : (1u << n_parts) - 1u;
   LiveLists lists = {nullptr, slots, ctx->d_live_list};
   DevView v = make_view(ctx, c);
-  if (H::turbo) {
+  if (H::turbo && n_parts == 1u) {
     int rc = refresh_scaled_table(ctx, c);
     if (rc) return rc;
   }
   const unsigned tgrid = (slots + 127) / 128;
   const uint32_t step_cap = ctx->opt.max_steps == 0 || ctx->opt.max_steps > 0xffffffffull ? 0xffffffffu
                                                                                          : (uint32_t)ctx->opt.max_steps;
+  const size_t n_counters = (size_t)n_parts * N_BIN_COUNTERS;
   double integrate_ms = 0.0;
   bool pending_timing = false;
   const bool trace = getenv("HEROAM_TRACE") != nullptr;  // per-pass bin populations and times on stderr
@@ -503,7 +557,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
   CU(cudaGetLastError());
   ctx->info.kernel_launches++;
   for (;;) {
-    CU(cudaMemsetAsync(ctx->d_bin_count, 0, N_BIN_COUNTERS * sizeof(uint32_t), ctx->main));
+    CU(cudaMemsetAsync(ctx->d_bin_count, 0, n_counters * sizeof(uint32_t), ctx->main));
     CU(cudaMemsetAsync(ctx->d_nbr_used, 0, sizeof(unsigned long long), ctx->main));
     const Segments sg = pass_segments(ctx, rg);
     if (lists.count)
@@ -511,7 +565,7 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
                                                                            ctx->d_bin_list, ctx->d_free_list, lists);
     CU(cudaGetLastError());
     ctx->info.kernel_launches++;
-    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, N_BIN_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
+    CU(cudaMemcpyAsync(ctx->h_bin_count, ctx->d_bin_count, n_counters * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->main));
     CU(cudaEventRecord(ctx->ev_r, ctx->main));
     CU(cudaStreamSynchronize(ctx->main));
     if (pending_timing) {
@@ -528,13 +582,23 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
         fprintf(stderr, " %.3f ms  psteps %llu free %llu resolve %.3f ms\n", (double)pass_ms, now.particle_steps, now.free_steps, ms);
       }
     }
-    uint64_t live = 0;
-    for (int b = 0; b < N_BINS; ++b) live += ctx->h_bin_count[b];
+    uint64_t live = 0, bin_total[N_BINS] = {};
+    for (uint32_t p = 0; p < n_parts; ++p)
+      for (int b = 0; b < N_BINS; ++b) {
+        bin_total[b] += ctx->h_bin_count[(size_t)p * N_BIN_COUNTERS + b];
+        live += ctx->h_bin_count[(size_t)p * N_BIN_COUNTERS + b];
+      }
     if (live == 0) break;  // every slot is free and the index space is used up
-    // a free slot claims a new trajectory in every pass while there are any: live < slots means none are left,
-    // and from then on only the slots listed as live need a visit
-    if (ctx->h_bin_count[LIVE_SLOT] < slots) pool.refill = 0;
-    update_regime(ctx, rg);
+    // a free slot claims a new trajectory in every pass while there are any: fewer live trajectories than slots
+    // means none are left (per part, in a partitioned pool); once that holds everywhere only the slots listed
+    // as live need a visit
+    if (n_parts == 1u) {
+      if (ctx->h_bin_count[LIVE_SLOT] < slots) pool.refill = 0;
+    } else {
+      for (uint32_t p = 0; p < n_parts; ++p)
+        if (ctx->h_bin_count[(size_t)p * N_BIN_COUNTERS + PART_LIVE_SLOT] < pool.slots_per_part) pool.refill &= ~(1u << p);
+    }
+    update_regime(ctx, rg, bin_total);
     if (!pool.refill) {
       lists.in = lists.out;
       lists.count = ctx->h_bin_count[LIVE_SLOT];
@@ -544,16 +608,28 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
     if (trace) {
       fprintf(stderr, "pass %llu live %llu behind %u bins", ctx->info.passes, (unsigned long long)live,
               0xffffffffu - ctx->h_bin_count[LAG_SLOT]);
-      for (int b = 1; b < N_BINS; ++b) fprintf(stderr, " %u", ctx->h_bin_count[b]);
+      for (int b = 1; b < N_BINS; ++b) fprintf(stderr, " %llu", (unsigned long long)bin_total[b]);
     }
     CU(cudaEventRecord(ctx->ev_i0, ctx->main));
     for (int b = 1; b < N_BINS; ++b) {
-      const uint32_t cnt = ctx->h_bin_count[b];
-      if (!cnt) continue;
+      if (!bin_total[b]) continue;
       CU(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_i0, 0));
-      int rc = launch_bin<H, F>(ctx, v, b, cnt, rg.draining);
-      if (rc) return rc;
-      ctx->info.kernel_launches++;
+      for (uint32_t p = 0; p < n_parts; ++p) {  // the parts of a bin share its stream: one after the other
+        const uint32_t cnt = ctx->h_bin_count[(size_t)p * N_BIN_COUNTERS + b];
+        if (!cnt) continue;
+        DevView vp = v;
+        uint32_t list_offset = 0, free_offset = 0;
+        if (n_parts > 1u) {
+          vp.c = parts.host[p].c;
+          vp.c.f_max = v.c.f_max;
+          vp.table_k = parts.host[p].table_k;
+          list_offset = p * pool.slots_per_part;
+          free_offset = p * pool.slots_per_part * pool.cap;
+        }
+        int rc = launch_bin<H, F>(ctx, vp, b, cnt, rg.draining, list_offset, free_offset);
+        if (rc) return rc;
+        ctx->info.kernel_launches++;
+      }
       CU(cudaEventRecord(ctx->bin_done[b], ctx->bin_stream[b]));
       CU(cudaStreamWaitEvent(ctx->main, ctx->bin_done[b], 0));
     }
@@ -564,12 +640,64 @@ static int run_pool(heroam_ctx *ctx, const Consts &c, const PoolParams &pool_in,
   return HEROAM_OK;
 }
 
+template <class T>
+static int run_pool_mode(heroam_ctx *ctx, const Consts &c, const PoolParams &pool, uint32_t slots, const T &parts) {
+  return ctx->opt.mode == HEROAM_MODE_EXACT          ? run_pool<Exact, Exact>(ctx, c, pool, slots, parts)
+         : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN   ? run_pool<Fast, Fast>(ctx, c, pool, slots, parts)
+         : ctx->opt.mode == HEROAM_MODE_FAST_RELAXED ? run_pool<Fast, Turbo8>(ctx, c, pool, slots, parts)
+         : ctx->opt.mode == HEROAM_MODE_FAST_CLOSED  ? run_pool<Fast, Turbo, TurboClosed>(ctx, c, pool, slots, parts)
+         : ctx->opt.count_work                     ? run_pool<Fast, TurboCount>(ctx, c, pool, slots, parts)
+                                                   : run_pool<Fast, Turbo>(ctx, c, pool, slots, parts);
+}
+
 static double point_lambda(const heroam_config &conf, unsigned long long he_number, float intensity, float pulse_width) {
   heroam_config c = conf;
   c.intensity = intensity;
   c.pulse_width = pulse_width;
   return host_lambda(c, he_number);
 }
+
+// the histograms and counters of a finished pool run, one block per point, onto the host
+static int collect_pool_stats(heroam_ctx *ctx, int rc, const DevStats *d_stats, int n_points, heroam_stats *out) {
+  std::vector<DevStats> h((size_t)n_points);
+  if (rc == HEROAM_OK) {
+    if (cudaMemcpyAsync(h.data(), d_stats, (size_t)n_points * sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
+        cudaEventRecord(ctx->ev_stop, ctx->main) != cudaSuccess || cudaStreamSynchronize(ctx->main) != cudaSuccess)
+      rc = fail(HEROAM_E_CUDA, "statistics readback failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (rc == HEROAM_OK) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+    ctx->info.device_ms = ms;
+    ctx->info.d2h_bytes = (size_t)n_points * sizeof(DevStats);
+    ctx->info.particle_steps = ctx->h_counters->particle_steps;
+    ctx->info.pair_steps = ctx->h_counters->pair_steps;
+    ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
+    ctx->info.pair_skipped = ctx->h_counters->pair_skipped;
+    ctx->info.free_steps = ctx->h_counters->free_steps;
+    for (int p = 0; p < n_points; ++p) {
+      ctx->info.trajectories += h[p].trajectories;
+      ctx->info.particles += h[p].particles;
+    }
+    for (int p = 0; p < n_points; ++p) {
+      memcpy(out[p].hist_n, h[p].hist_n, sizeof out[p].hist_n);
+      memcpy(out[p].hist_traj_time, h[p].hist_traj_time, sizeof out[p].hist_traj_time);
+      memcpy(out[p].hist_meet_time, h[p].hist_meet_time, sizeof out[p].hist_meet_time);
+      memcpy(out[p].done, h[p].done, sizeof out[p].done);
+      out[p].unmet_particles = h[p].unmet_particles;
+      out[p].particles = h[p].particles;
+      out[p].trajectories = h[p].trajectories;
+      out[p].sum_traj_time = (double)h[p].sum_traj_time_q10 / 1024.0;
+      out[p].info = ctx->info;  // work and timing of the whole sweep
+    }
+    if (ctx->h_counters->unsupported)
+      rc = fail(HEROAM_E_UNSUPPORTED, "%llu trajectories have more than %d particles", ctx->h_counters->unsupported,
+                MAX_ACTIVE);
+  }
+  return rc;
+}
+
 
 extern "C" int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_number, int n_points,
                                     const heroam_sweep_point *points, heroam_stats *out) {
@@ -630,49 +758,8 @@ extern "C" int heroam_gpu_run_sweep(heroam_ctx *ctx, unsigned long long he_numbe
   CU(cudaMemsetAsync(d_stats, 0, (size_t)n_points * sizeof(DevStats), ctx->main));
   CU(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->main));
   CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
-  rc = ctx->opt.mode == HEROAM_MODE_EXACT          ? run_pool<Exact, Exact>(ctx, c, pool, slots)
-       : ctx->opt.mode == HEROAM_MODE_FAST_PLAIN   ? run_pool<Fast, Fast>(ctx, c, pool, slots)
-       : ctx->opt.mode == HEROAM_MODE_FAST_RELAXED ? run_pool<Fast, Turbo8>(ctx, c, pool, slots)
-       : ctx->opt.mode == HEROAM_MODE_FAST_CLOSED  ? run_pool<Fast, Turbo, TurboClosed>(ctx, c, pool, slots)
-       : ctx->opt.count_work                     ? run_pool<Fast, TurboCount>(ctx, c, pool, slots)
-                                                 : run_pool<Fast, Turbo>(ctx, c, pool, slots);
-  std::vector<DevStats> h((size_t)n_points);
-  if (rc == HEROAM_OK) {
-    if (cudaMemcpyAsync(h.data(), d_stats, (size_t)n_points * sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
-        cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->main) != cudaSuccess ||
-        cudaEventRecord(ctx->ev_stop, ctx->main) != cudaSuccess || cudaStreamSynchronize(ctx->main) != cudaSuccess)
-      rc = fail(HEROAM_E_CUDA, "statistics readback failed: %s", cudaGetErrorString(cudaGetLastError()));
-  }
-  if (rc == HEROAM_OK) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
-    ctx->info.device_ms = ms;
-    ctx->info.d2h_bytes = (size_t)n_points * sizeof(DevStats);
-    ctx->info.particle_steps = ctx->h_counters->particle_steps;
-    ctx->info.pair_steps = ctx->h_counters->pair_steps;
-    ctx->info.inrange_steps = ctx->h_counters->inrange_steps;
-    ctx->info.pair_skipped = ctx->h_counters->pair_skipped;
-    ctx->info.free_steps = ctx->h_counters->free_steps;
-    for (int p = 0; p < n_points; ++p) {
-      ctx->info.trajectories += h[p].trajectories;
-      ctx->info.particles += h[p].particles;
-    }
-    for (int p = 0; p < n_points; ++p) {
-      memcpy(out[p].hist_n, h[p].hist_n, sizeof out[p].hist_n);
-      memcpy(out[p].hist_traj_time, h[p].hist_traj_time, sizeof out[p].hist_traj_time);
-      memcpy(out[p].hist_meet_time, h[p].hist_meet_time, sizeof out[p].hist_meet_time);
-      memcpy(out[p].done, h[p].done, sizeof out[p].done);
-      out[p].unmet_particles = h[p].unmet_particles;
-      out[p].particles = h[p].particles;
-      out[p].trajectories = h[p].trajectories;
-      out[p].sum_traj_time = h[p].sum_traj_time;
-      out[p].info = ctx->info;  // work and timing of the whole sweep
-    }
-    if (ctx->h_counters->unsupported)
-      rc = fail(HEROAM_E_UNSUPPORTED, "%llu trajectories have more than %d particles", ctx->h_counters->unsupported,
-                MAX_ACTIVE);
-  }
-  return rc;
+  rc = run_pool_mode(ctx, c, pool, slots, PoolParts());
+  return collect_pool_stats(ctx, rc, d_stats, n_points, out);
 }
 
 extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_number, unsigned long long first_index,
@@ -684,4 +771,101 @@ extern "C" int heroam_gpu_run_stats(heroam_ctx *ctx, unsigned long long he_numbe
   point.first_index = first_index;
   point.count = count;
   return heroam_gpu_run_sweep(ctx, he_number, 1, &point, out);
+}
+
+// ---------------------------------------------------------------------------------
+// The reference's own sweep, over droplet sizes (main.c:158-164), as ONE run of the pool: every size has its own
+// sphere radius, hence its own constants and its own kappa-scaled table copy, so the pool is partitioned -- each
+// size owns an equal share of the slots and its own bin lists (PartParams, PartSlice) -- and all sizes share the
+// passes: one drain for the whole sweep instead of one per size.
+// ---------------------------------------------------------------------------------
+extern "C" int heroam_gpu_run_size_sweep(heroam_ctx *ctx, int n_points, const heroam_size_point *points, heroam_stats *out) {
+  if (!ctx || !out || !points) return fail(HEROAM_E_ARG, "heroam_gpu_run_size_sweep: null argument");
+  if (n_points < 1 || n_points > MAX_PARTS)
+    return fail(HEROAM_E_ARG, "heroam_gpu_run_size_sweep: %d sizes (1..%d supported per call)", n_points, MAX_PARTS);
+  if (n_points == 1) return heroam_gpu_run_stats(ctx, points[0].he_number, points[0].first_index, points[0].count, out);
+  CU(cudaSetDevice(ctx->device));
+  memset(out, 0, (size_t)n_points * sizeof *out);
+  memset(&ctx->info, 0, sizeof ctx->info);
+  ctx->uploaded = false;
+  PoolParts parts;
+  parts.host.resize((size_t)n_points);
+  double lambda_max = 0.0;
+  unsigned long long count_max = 0, total = 0;
+  for (int p = 0; p < n_points; ++p) {
+    PartParams &pp = parts.host[p];
+    int rc = make_consts(ctx->conf, points[p].he_number, &pp.c);
+    if (rc) return rc;
+    pp.c.f_max = ctx->f_max;
+    const double lambda = host_lambda(ctx->conf, points[p].he_number);
+    if (!(lambda > 0.0) || lambda > 700.0)
+      return fail(HEROAM_E_ARG, "mean excitation number %g outside (0, 700]: Knuth's product of uniforms "
+                  "(simulation.c:257-275) is undefined there", lambda);
+    if (lambda > lambda_max) lambda_max = lambda;
+    pp.he_number = points[p].he_number;
+    pp.first_index = points[p].first_index;
+    pp.count = points[p].count;
+    pp.limit = exp(-1.0 * lambda);
+    pp.radius_init = 2.22 * pow((double)points[p].he_number, 1.0 / 3.0);
+    pp.table_k = nullptr;
+    if (pp.count > count_max) count_max = pp.count;
+    total += pp.count;
+  }
+  if (total == 0) return HEROAM_OK;
+  const uint32_t cap = pool_slot_capacity(lambda_max);
+  const unsigned long long pool_max = ctx->opt.pool_slots > 0 ? (unsigned long long)ctx->opt.pool_slots : (1ull << 22);
+  // equal shares of the pool, whole blocks of the resolve kernel, no more than the largest part needs
+  unsigned long long per_part = pool_max / (unsigned long long)n_points;
+  if (per_part > count_max) per_part = count_max;
+  per_part = (per_part + 127ull) / 128ull * 128ull;
+  const uint32_t slots = (uint32_t)(per_part * (unsigned long long)n_points);
+  if ((unsigned long long)slots * cap > 0xfffffff0ull)
+    return fail(HEROAM_E_ARG, "%u pool slots with %u records per slot exceed 2^32 particle records", slots, cap);
+  int rc = reserve(ctx, slots, (size_t)slots * cap);
+  if (rc) return rc;
+  ctx->he_number = points[0].he_number;
+  ctx->n_traj = slots;
+  ctx->n_particles = (size_t)slots * cap;
+  // one kappa-scaled copy of the table per size (Turbo kernels)
+  const unsigned table_n = (unsigned)ctx->table_len + 1u;
+  DevBuf<float> scaled;
+  CU(scaled.alloc((size_t)n_points * table_n));
+  for (int p = 0; p < n_points; ++p) {
+    float *dst = scaled.ptr + (size_t)p * table_n;
+    k_scale_table<<<(table_n + 255u) / 256u, 256, 0, ctx->main>>>(dst, ctx->d_table, table_n, parts.host[p].c.kappa);
+    CU(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    parts.host[p].table_k = dst;
+  }
+  DevBuf<PartParams> d_parts;
+  DevBuf<DevStats> stats_buf;
+  DevBuf<unsigned long long> cursor_buf;
+  CU(d_parts.alloc((size_t)n_points));
+  CU(stats_buf.alloc((size_t)n_points));
+  CU(cursor_buf.alloc((size_t)n_points));
+  CU(cudaMemcpyAsync(d_parts.ptr, parts.host.data(), (size_t)n_points * sizeof(PartParams), cudaMemcpyHostToDevice, ctx->main));
+  PoolParams pool;
+  memset(&pool, 0, sizeof pool);
+  pool.sp.seed = (long long)ctx->conf.seed;
+  pool.sp.he_number = points[0].he_number;
+  pool.sp.first_index = 0;
+  pool.sp.limit = parts.host[0].limit;
+  pool.sp.radius_init = parts.host[0].radius_init;
+  pool.sp.sigma = ctx->conf.velocity;
+  pool.cursor = cursor_buf.ptr;
+  pool.count = total;
+  pool.cap = cap;
+  pool.n_points = (uint32_t)n_points;
+  pool.stats = stats_buf.ptr;
+  pool.n_parts = (uint32_t)n_points;
+  pool.slots_per_part = (uint32_t)per_part;
+  pool.parts = d_parts.ptr;
+  CU(cudaEventRecord(ctx->ev_start, ctx->main));
+  CU(cudaMemsetAsync(stats_buf.ptr, 0, (size_t)n_points * sizeof(DevStats), ctx->main));
+  CU(cudaMemsetAsync(cursor_buf.ptr, 0, (size_t)n_points * sizeof(unsigned long long), ctx->main));
+  CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->main));
+  rc = run_pool_mode(ctx, parts.host[0].c, pool, slots, parts);
+  rc = collect_pool_stats(ctx, rc, stats_buf.ptr, n_points, out);
+  CU(cudaStreamSynchronize(ctx->main));  // the scaled tables and part records go out of scope here
+  return rc;
 }

@@ -54,6 +54,7 @@ ABI_SYMBOLS = (
     "heroam_gpu_free_particles",
     "heroam_gpu_run_stats",
     "heroam_gpu_run_sweep",
+    "heroam_gpu_run_size_sweep",
     "heroam_gpu_last_run_info",
     "heroam_gpu_fp32_peak",
     "heroam_gpu_fp32_peak_rrr",
@@ -123,6 +124,10 @@ class SweepPoint(C.Structure):
                 ("count", C.c_ulonglong)]
 
 
+class SizePoint(C.Structure):
+    _fields_ = [("he_number", C.c_ulonglong), ("first_index", C.c_ulonglong), ("count", C.c_ulonglong)]
+
+
 _lib = None
 
 
@@ -169,6 +174,8 @@ def load_library() -> C.CDLL:
     L.heroam_gpu_run_stats.argtypes = [vp, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.POINTER(Stats)]
     L.heroam_gpu_run_sweep.restype = C.c_int
     L.heroam_gpu_run_sweep.argtypes = [vp, C.c_ulonglong, C.c_int, C.POINTER(SweepPoint), C.POINTER(Stats)]
+    L.heroam_gpu_run_size_sweep.restype = C.c_int
+    L.heroam_gpu_run_size_sweep.argtypes = [vp, C.c_int, C.POINTER(SizePoint), C.POINTER(Stats)]
     L.heroam_gpu_last_run_info.restype = C.c_int
     L.heroam_gpu_last_run_info.argtypes = [vp, C.POINTER(RunInfo)]
     L.heroam_gpu_fp32_peak.restype = C.c_int
@@ -342,6 +349,16 @@ class Engine:
             a.intensity, a.pulse_width, a.count, a.first_index = intensity, pulse_width, count, first_index
         out = (Stats * len(points))()
         self._check(self.lib.heroam_gpu_run_sweep(self.handle, he_number, len(points), arr, out))
+        return [self._stats_dict(st) for st in out]
+
+    def run_size_sweep(self, points) -> list:
+        """``heroam_gpu_run_size_sweep``: points = [(he_number, count, first_index), ...] -- the reference's
+        droplet-size sweep (main.c:158-164) as one pool run; one statistics dict per size."""
+        arr = (SizePoint * len(points))()
+        for a, (he_number, count, first_index) in zip(arr, points):
+            a.he_number, a.count, a.first_index = he_number, count, first_index
+        out = (Stats * len(points))()
+        self._check(self.lib.heroam_gpu_run_size_sweep(self.handle, len(points), arr, out))
         return [self._stats_dict(st) for st in out]
 
     def run_stats(self, he_number: int, count: int, first_index: int = 0) -> dict:

@@ -56,6 +56,30 @@ def test_heroam_cli_writes_reference_files(tmp_path, port, table):
     assert (tmp_path / "results" / "histograms_10000.tsv").exists()
 
 
+def test_heroam_cli_size_sweep_as_one_run(tmp_path):
+    """start/step/stop with HEROAM_STATS=1: all droplet sizes in one pool run, one histogram file per size, equal
+    to the files of the sizes run one by one."""
+    if engine.device_count() < 1:
+        pytest.fail("needs a CUDA device")
+    exe = os.path.join(ROOT, "host", "HeRoam")
+    conf_text = open(os.path.join(ROOT, "host", "config.example.conf")).read()
+    conf_text = conf_text.replace("\nnumber = 1000", "\nnumber = 600").replace("max_time = 10000000", "max_time = 20000")
+    sweep = conf_text.replace("\nstart = 0", "\nstart = 6000").replace("\nstep = 0", "\nstep = 4000").replace("\nstop = 0", "\nstop = 14001")
+    assert sweep != conf_text
+    (tmp_path / "sweep.conf").write_text(sweep)
+    env = dict(os.environ, HEROAM_STATS="1", HEROAM_MODE="exact")
+    r = subprocess.run([exe, "sweep.conf"], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    assert "3 droplet sizes as one run" in r.stdout
+    for n in (6000, 10000, 14000):
+        one = conf_text.replace("helium_number = 10000", f"helium_number = {n}")
+        (tmp_path / "one.conf").write_text(one)
+        os.rename(tmp_path / "results" / f"histograms_{n}.tsv", tmp_path / f"swept_{n}.tsv")
+        r = subprocess.run([exe, "one.conf"], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr
+        assert (tmp_path / "results" / f"histograms_{n}.tsv").read_bytes() == (tmp_path / f"swept_{n}.tsv").read_bytes(), n
+
+
 def test_reference_named_interface(port, table):
     conf = make_config(number=48, max_time=1.0e4)
     batch = simulation.initialize_particles(10000, conf, table)

@@ -71,3 +71,36 @@ def test_shard_sweep_partitions_every_point():
                 assert s[p][3] == at
                 at += s[p][2]
             assert at == first + count
+
+
+# The reference's own sweep, over droplet sizes (main.c:158-164), as one run of the partitioned pool
+SIZE_POINTS = [(6000, 2500, 0), (10000, 3000, 50), (16000, 1200, 7), (30000, 900, 123456789012)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,pool_slots", [("exact", 0), ("exact", 1024), ("fast", 0), ("fast", 2048)])
+def test_size_sweep_equals_separate_runs(table, mode, pool_slots):
+    """Every droplet size of heroam_gpu_run_size_sweep -- its own sphere radius, constants and scaled table copy,
+    sharing the passes of one pool run with the other sizes -- must equal that size run on its own."""
+    max_time = 3.0e4
+    with engine.Engine(make_config(max_time=max_time), table, mode=mode, pool_slots=pool_slots) as eng:
+        swept = eng.run_size_sweep(SIZE_POINTS)
+        info = swept[0]["info"]
+        singles = [eng.run_stats(he, count, first_index=first) for he, count, first in SIZE_POINTS]
+    assert len(swept) == len(SIZE_POINTS)
+    for (he, count, first), got, want in zip(SIZE_POINTS, swept, singles):
+        assert_same_stats(got, want, f"N_He = {he}")
+    assert info["trajectories"] == sum(p[1] for p in SIZE_POINTS)
+    assert info["particle_steps"] == sum(s["info"]["particle_steps"] for s in singles)
+    # different sizes do differ (the sweep is not one size four times over)
+    assert not np.array_equal(swept[0]["hist_meet_time"], swept[3]["hist_meet_time"])
+
+
+@pytest.mark.gpu
+def test_size_sweep_argument_checks(table):
+    with engine.Engine(make_config(), table) as eng:
+        with pytest.raises(engine.HeroamError, match="sizes"):
+            eng.run_size_sweep([(10000, 1, 0)] * 33)
+        one = eng.run_size_sweep([(10000, 40, 3)])
+        assert one[0]["trajectories"] == 40
+        assert eng.run_size_sweep([(10000, 0, 0), (20000, 0, 0)])[1]["trajectories"] == 0
