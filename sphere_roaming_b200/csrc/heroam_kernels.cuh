@@ -358,7 +358,25 @@ struct Reach {
   float RdtW, accel, slack, d_far;
   float w0[MAX_ACTIVE];
   uint8_t deg[MAX_ACTIVE];
+  // Candidate pairs: the pairs that would be linked if every particle had the largest reach it can have (every other
+  // particle a partner).  Only they can ever be linked, so the fixed point is iterated over them alone: one sweep over
+  // all pairs per analysis instead of one per iteration.  On a large droplet (config C3: 49 particles on R = 478 A,
+  // 99 % of the pairs out of reach) that is a handful of pairs out of 1176, and the resolve kernel -- one thread per
+  // trajectory, 59 % of the run before -- no longer dominates it.  Dense trajectories that overflow the list keep the
+  // all-pairs iteration.
+  static constexpr uint32_t CAND_CAP = 320;
+  // positions copied once into the thread's own (lane-interleaved, hence coalesced) local memory: the sweep over
+  // all pairs would otherwise re-read the 84-byte records of 32 different trajectories per warp instruction
+  float px[MAX_ACTIVE], py[MAX_ACTIVE], pz[MAX_ACTIVE];
+  uint8_t cj[CAND_CAP], ck[CAND_CAP];
+  float cgap[CAND_CAP];
+  uint32_t n_cand;
+  bool dense;  // the candidates did not fit: iterate over all pairs
 
+  __device__ float gap_of(uint32_t j, uint32_t k) const {
+    const float dx = px[j] - px[k], dy = py[j] - py[k], dz = pz[j] - pz[k];
+    return sqrtf(dx * dx + dy * dy + dz * dz) - d_far;
+  }
   __device__ void init(const DevView &v, const TrajMeta &m, uint32_t count, uint32_t window) {
     base = v.particles + m.first;
     act = v.act + m.first;
@@ -369,34 +387,71 @@ struct Reach {
     accel = 0.5f * R * dt * dt * v.c.f_max * v.c.inv_mr * W * W * 1.02f; // extra path per linked partner
     slack = 2.0e-6f * R * W + 2.0e-3f;
     for (uint32_t s = 0; s < a; ++s) {
-      const float *w = base[act[s]].ang_velocity;
+      const heroam_particle *p = base + act[s];
+      const float *w = p->ang_velocity;
       w0[s] = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+      px[s] = p->position[0]; py[s] = p->position[1]; pz[s] = p->position[2];
       deg[s] = 0;
+    }
+    // one sweep over all pairs, squared distances against the squared largest possible limit (with margin: the
+    // exact test below decides, this only has to be a superset)
+    n_cand = 0;
+    dense = false;
+    const float most = (float)(a - 1u) * accel + slack;
+    for (uint32_t j = 0; j + 1 < a && !dense; ++j) {
+      const float xj = px[j], yj = py[j], zj = pz[j], lj = d_far + fmaf(w0[j], RdtW, most);
+      for (uint32_t k = j + 1; k < a; ++k) {
+        const float dx = xj - px[k], dy = yj - py[k], dz = zj - pz[k];
+        const float lim = (lj + fmaf(w0[k], RdtW, most)) * 1.0001f;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 <= lim * lim) {
+          if (n_cand == CAND_CAP) { dense = true; break; }
+          cj[n_cand] = (uint8_t)j;
+          ck[n_cand] = (uint8_t)k;
+          cgap[n_cand] = sqrtf(d2) - d_far;
+          ++n_cand;
+        }
+      }
     }
   }
   __device__ float reach(uint32_t s) const { return fmaf(w0[s], RdtW, fmaf((float)deg[s], accel, slack)); }
-  __device__ float dist(uint32_t j, uint32_t k) const {
-    const float *pj = base[act[j]].position, *pk = base[act[k]].position;
-    const float dx = pj[0] - pk[0], dy = pj[1] - pk[1], dz = pj[2] - pk[2];
-    return sqrtf(dx * dx + dy * dy + dz * dz);
-  }
-  __device__ bool linked(uint32_t j, uint32_t k) const { return dist(j, k) - d_far <= reach(j) + reach(k); }
+  __device__ bool linked(uint32_t j, uint32_t k) const { return gap_of(j, k) <= reach(j) + reach(k); }
   __device__ void solve() {
     for (int iter = 0; iter < 16; ++iter) {
       bool grew = false;
-      // one sweep over unordered pairs: count links with the current reaches
+      // count links with the current reaches
       uint8_t cnt[MAX_ACTIVE];
       for (uint32_t s = 0; s < a; ++s) cnt[s] = 0;
-      for (uint32_t j = 0; j + 1 < a; ++j) {
-        const float rj = reach(j);
-        for (uint32_t k = j + 1; k < a; ++k)
-          if (dist(j, k) - d_far <= rj + reach(k)) { ++cnt[j]; ++cnt[k]; }
+      if (!dense) {
+        for (uint32_t i = 0; i < n_cand; ++i)
+          if (cgap[i] <= reach(cj[i]) + reach(ck[i])) { ++cnt[cj[i]]; ++cnt[ck[i]]; }
+      } else {
+        for (uint32_t j = 0; j + 1 < a; ++j) {
+          const float rj = reach(j);
+          for (uint32_t k = j + 1; k < a; ++k)
+            if (gap_of(j, k) <= rj + reach(k)) { ++cnt[j]; ++cnt[k]; }
+        }
       }
       for (uint32_t s = 0; s < a; ++s)
         if (cnt[s] > deg[s]) { deg[s] = cnt[s]; grew = true; }
       if (!grew) return;
     }
     for (uint32_t s = 0; s < a; ++s) deg[s] = (uint8_t)(a - 1);  // no fixed point in time: link everything
+  }
+  // the partners of slot s at the fixed point, ascending, at most deg[s] of them; returns how many
+  __device__ uint32_t partners(uint32_t s, uint8_t *out) const {
+    uint32_t n = 0;
+    if (!dense) {
+      // the candidates are in (j, k) order: those with k == s come first (ascending j < s), then those with j == s
+      for (uint32_t i = 0; i < n_cand && n < deg[s]; ++i) {
+        const uint32_t j = cj[i], k = ck[i];
+        if ((j == s || k == s) && cgap[i] <= reach(j) + reach(k)) out[n++] = (uint8_t)(j == s ? k : j);
+      }
+    } else {
+      for (uint32_t k = 0; k < a && n < deg[s]; ++k)
+        if (k != s && linked(s < k ? s : k, s < k ? k : s)) out[n++] = (uint8_t)k;
+    }
+    return n;
   }
   __device__ bool force_free(uint32_t s) const {
     const float *f = base[act[s]].force;
@@ -453,10 +508,7 @@ __device__ inline void build_partner_lists(const DevView &v, const TrajMeta &m, 
   unsigned long long cursor = at;
   for (uint32_t j = 0; j < a; ++j) {
     v.nbr_start[m.first + j] = (uint32_t)cursor;
-    uint32_t n = 0;
-    for (uint32_t k = 0; k < a && n < rc.deg[j]; ++k)
-      if (k != j && rc.linked(j, k)) v.nbr_pool[cursor + n++] = (uint8_t)k;
-    v.nbr_cnt[m.first + j] = n;
+    v.nbr_cnt[m.first + j] = rc.partners(j, v.nbr_pool + cursor);
     cursor += rc.deg[j];
   }
 }
