@@ -1,8 +1,11 @@
-"""Drain experiments (GPU only): one pooled run of N trajectories of config C2 per setting, same
-index block, so every setting must return identical histograms.
+"""Run-level experiments (GPU only): one pooled run of N trajectories of config C2 per setting, same
+index block, so every setting must return identical histograms (in the modes that are schedule-independent).
 
-    N=1000000 SETTINGS="off;on;on,us=5000;on,seg=2048" python scripts/drain_probe.py
-"""
+    N=1000000 SETTINGS="on;base=4096;base=16384" MODE=fast python scripts/drain_probe.py
+
+Tokens: on (defaults), base=<segment_steps>, labulk=<w> (env HEROAM_LOOKAHEAD_BULK: the L1-prefetch variant of the
+thread kernels for widths <= w also while the GPU is full).  HEROAM_TRACE=1 prints one line per pass on stderr
+(scripts/trace_view.py reads it)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,20 +16,12 @@ from sphere_roaming_b200.types import make_config
 N = int(os.environ.get("N", 1000000)); MT = float(os.environ.get("MT", 1e7)); MODE = os.environ.get("MODE", "fast")
 table = synthetic_table()
 ref = None
-for setting in os.environ.get("SETTINGS", "off;on").split(";"):
+for setting in os.environ.get("SETTINGS", "on").split(";"):
     kw = {}
-    for k in ("HEROAM_DRAIN_PER_SM", "HEROAM_DRAIN_LIVE_PER_SM", "HEROAM_BULK_SLICE_CAP_US", "HEROAM_BULK_SEG_MULT", "HEROAM_NOSPLIT_MAX", "HEROAM_X_NOFAR", "HEROAM_X_NOEXACT", "HEROAM_LOOKAHEAD_BULK"):
-        os.environ.pop(k, None)
+    os.environ.pop("HEROAM_LOOKAHEAD_BULK", None)
     for tok in setting.split(","):
-        if tok == "on": pass
-        elif tok.startswith("base="): kw["segment_steps"] = int(tok[5:])
-        elif tok.startswith("live="): os.environ["HEROAM_DRAIN_LIVE_PER_SM"] = tok[5:]
-        elif tok.startswith("cap="): os.environ["HEROAM_BULK_SLICE_CAP_US"] = tok[4:]
-        elif tok.startswith("mult="): os.environ["HEROAM_BULK_SEG_MULT"] = tok[5:]
-        elif tok.startswith("nosplit="): os.environ["HEROAM_NOSPLIT_MAX"] = tok[8:]
-        elif tok == "nofar": os.environ["HEROAM_X_NOFAR"] = "1"
+        if tok.startswith("base="): kw["segment_steps"] = int(tok[5:])
         elif tok.startswith("labulk="): os.environ["HEROAM_LOOKAHEAD_BULK"] = tok[7:]
-        elif tok == "noexact": os.environ["HEROAM_X_NOEXACT"] = "1"
     with engine.Engine(make_config(number=N, max_time=MT), table, mode=MODE, **kw) as eng:
         if ref is None:
             eng.run_stats(10000, min(N, 100000), first_index=10**9)  # warm-up
