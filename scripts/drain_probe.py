@@ -3,8 +3,7 @@ index block, so every setting must return identical histograms (in the modes tha
 
     N=1000000 SETTINGS="on;base=4096;base=16384" MODE=fast python scripts/drain_probe.py
 
-Tokens: on (defaults), base=<segment_steps>, labulk=<w> (env HEROAM_LOOKAHEAD_BULK: the L1-prefetch variant of the
-thread kernels for widths <= w also while the GPU is full).  HEROAM_TRACE=1 prints one line per pass on stderr
+Tokens: on (defaults), base=<segment_steps>.  HEROAM_TRACE=1 prints one line per pass on stderr
 (scripts/trace_view.py reads it)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,10 +17,8 @@ table = synthetic_table()
 ref = None
 for setting in os.environ.get("SETTINGS", "on").split(";"):
     kw = {}
-    os.environ.pop("HEROAM_LOOKAHEAD_BULK", None)
     for tok in setting.split(","):
         if tok.startswith("base="): kw["segment_steps"] = int(tok[5:])
-        elif tok.startswith("labulk="): os.environ["HEROAM_LOOKAHEAD_BULK"] = tok[7:]
     with engine.Engine(make_config(number=N, max_time=MT), table, mode=MODE, **kw) as eng:
         if ref is None:
             eng.run_stats(10000, min(N, 100000), first_index=10**9)  # warm-up
