@@ -414,11 +414,6 @@ struct Regime {
   bool draining = false;      // fewer trajectories in the full kernels than fill the GPU: latency-bound segment table
 };
 
-static int env_int(const char *name, int fallback) {
-  const char *e = getenv(name);
-  return e && *e ? atoi(e) : fallback;
-}
-
 // What a pass is launched with under regime rg.
 static Segments pass_segments(const heroam_ctx *ctx, const Regime &rg) {
   Segments sg = make_segments(ctx->opt.segment_steps, rg.draining, split_window_max(ctx));
