@@ -42,7 +42,7 @@ constexpr int N_BIN_COUNTERS = N_BINS + 3;
 constexpr int MAX_PARTS = 32;              // parts of a partitioned pool (a droplet-size sweep as one run)
 constexpr int FREE_MAX_A = 8;     // the free-flight analysis is done for trajectories with <= 8 moving particles
 constexpr int MAX_ACTIVE = 128;   // wider trajectories are refused (HEROAM_DONE_UNSUPPORTED)
-constexpr int INTEGRATE_TPB = 128;
+constexpr int INTEGRATE_TPB = 128;  // 64 was measured too (round 2): no gain
 constexpr int SMEM_TPB = 64;          // threads (= trajectories) per block of k_integrate_smem / k_integrate_hybrid
 constexpr int WARP_KERNEL_WARPS = 4;  // warps (= trajectories) per block of k_integrate_warp
 
