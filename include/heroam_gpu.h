@@ -176,6 +176,12 @@ int heroam_gpu_simulate_batch(heroam_ctx *ctx, unsigned long long he_number,
                               heroam_particles *trajectories, int count,
                               heroam_traj_result *results);
 
+/* Optional: size the device buffers and the page-locked staging of heroam_gpu_simulate_batch for batches of up
+ * to n_trajectories trajectories / n_records particle records ahead of time, so that the first large call does
+ * not pay for the allocations (they otherwise grow on demand and are kept).  The reference allocates per call
+ * (main.c:55, simulation.c:310). */
+int heroam_gpu_reserve(heroam_ctx *ctx, unsigned long long n_trajectories, unsigned long long n_records);
+
 /* Same on a flat batch: counts[count] particles per trajectory, records stored
  * trajectory after trajectory in flat[]. */
 int heroam_gpu_simulate_flat(heroam_ctx *ctx, unsigned long long he_number,

@@ -663,6 +663,25 @@ static void stage_parallel(heroam_particles *trajectories, const std::vector<siz
   for (auto &th : pool) th.join();
 }
 
+static int reserve_stage(heroam_ctx *ctx, size_t records) {
+  if (records <= ctx->cap_stage) return HEROAM_OK;
+  cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr;
+  ctx->cap_stage = 0;
+  CU(cudaMallocHost(&ctx->h_stage, records * sizeof(heroam_particle)));
+  ctx->cap_stage = records;
+  return HEROAM_OK;
+}
+
+extern "C" int heroam_gpu_reserve(heroam_ctx *ctx, unsigned long long n_trajectories, unsigned long long n_records) {
+  if (!ctx) return fail(HEROAM_E_ARG, "null context");
+  if (n_records > 0xfffffff0ull || n_trajectories > 0xfffffff0ull) return fail(HEROAM_E_ARG, "batch too large: more than 2^32 records");
+  CU(cudaSetDevice(ctx->device));
+  int rc = reserve(ctx, n_trajectories ? (size_t)n_trajectories : 1, n_records ? (size_t)n_records : 1);
+  if (rc) return rc;
+  return reserve_stage(ctx, (size_t)n_records);
+}
+
 extern "C" int heroam_gpu_simulate_batch(heroam_ctx *ctx, unsigned long long he_number,
                                          heroam_particles *trajectories, int count, heroam_traj_result *results) {
   if (!ctx || (!trajectories && count > 0) || count < 0) return fail(HEROAM_E_ARG, "heroam_gpu_simulate_batch: bad argument");
@@ -677,15 +696,10 @@ extern "C" int heroam_gpu_simulate_batch(heroam_ctx *ctx, unsigned long long he_
     first[i] = total;
     total += counts[i];
   }
-  if (total > ctx->cap_stage) {
-    cudaFreeHost(ctx->h_stage);
-    ctx->h_stage = nullptr;
-    ctx->cap_stage = 0;
-    CU(cudaMallocHost(&ctx->h_stage, total * sizeof(heroam_particle)));
-    ctx->cap_stage = total;
-  }
+  int rc = reserve_stage(ctx, total);
+  if (rc) return rc;
   stage_parallel(trajectories, first, ctx->h_stage, count, true);
-  int rc = heroam_gpu_simulate_flat(ctx, he_number, counts.data(), ctx->h_stage, count, results);
+  rc = heroam_gpu_simulate_flat(ctx, he_number, counts.data(), ctx->h_stage, count, results);
   if (rc) return rc;
   stage_parallel(trajectories, first, ctx->h_stage, count, false);
   return HEROAM_OK;

@@ -44,6 +44,7 @@ ABI_SYMBOLS = (
     "heroam_gpu_destroy",
     "heroam_gpu_set_mode",
     "heroam_gpu_simulate_batch",
+    "heroam_gpu_reserve",
     "heroam_gpu_simulate_flat",
     "heroam_gpu_simulate_traced",
     "heroam_gpu_upload",
@@ -154,6 +155,8 @@ def load_library() -> C.CDLL:
     L.heroam_gpu_set_mode.argtypes = [vp, C.c_int]
     L.heroam_gpu_simulate_batch.restype = C.c_int
     L.heroam_gpu_simulate_batch.argtypes = [vp, C.c_ulonglong, C.POINTER(ParticlesC), C.c_int, vp]
+    L.heroam_gpu_reserve.restype = C.c_int
+    L.heroam_gpu_reserve.argtypes = [vp, C.c_ulonglong, C.c_ulonglong]
     L.heroam_gpu_simulate_flat.restype = C.c_int
     L.heroam_gpu_simulate_flat.argtypes = [vp, C.c_ulonglong, u32p, vp, C.c_int, vp]
     L.heroam_gpu_simulate_traced.restype = C.c_int
@@ -285,6 +288,10 @@ class Engine:
         assert counts.flags.c_contiguous and flat.flags.c_contiguous and results.flags.c_contiguous
         self._check(self.lib.heroam_gpu_simulate_flat(self.handle, he_number, counts.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                       flat.ctypes.data, len(counts), results.ctypes.data))
+
+    def reserve(self, n_trajectories: int, n_records: int) -> None:
+        """``heroam_gpu_reserve``: size device buffers and staging ahead of the first large batch."""
+        self._check(self.lib.heroam_gpu_reserve(self.handle, n_trajectories, n_records))
 
     def simulate_batch_inplace(self, he_number: int, particles: np.ndarray, results: np.ndarray) -> None:
         """``heroam_gpu_simulate_batch`` on an array of the reference's ``Particles`` headers

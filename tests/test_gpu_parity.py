@@ -226,8 +226,11 @@ def test_simulate_batch_reference_layout(need_gpu, port, table):
         arr[i].no, arr[i].index, arr[i].particle = int(counts[i]), i, bufs[i].ctypes.data
     res = np.zeros(n, dtype=engine.RESULT_DTYPE)
     with engine.Engine(conf, table, mode="exact") as eng:
+        eng.reserve(2 * n, 2 * len(init))  # heroam_gpu_reserve: buffers sized ahead, results unchanged
         rc = eng.lib.heroam_gpu_simulate_batch(eng.handle, HE, arr, n, res.ctypes.data)
         assert rc == 0, eng.lib.heroam_gpu_last_error()
+        with pytest.raises(engine.HeroamError):
+            eng.reserve(1, 2**32)
     assert_records_equal(np.concatenate(bufs), want, "simulate_batch")
     assert np.array_equal(res["steps"], wres["steps"])
 
