@@ -8,6 +8,11 @@ out = []
 P = out.append
 
 
+def src(f):
+    """A capture as brought back in gpurun_out/, else the copy already committed under profiles/."""
+    return os.path.join(G, f) if os.path.exists(os.path.join(G, f)) else os.path.join(PROF, f)
+
+
 def read_rows(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     for i, r in enumerate(rows):
@@ -103,29 +108,41 @@ P("All captures with `--clock-control none`, each after the same command had exi
   "variant of the latency-bound regime, of `k_free_flight` = clock set at landing (DESIGN.md sections 3-4).\n")
 P("## 1. Launch list of the bench command\n")
 SMALL = "--steps 2 --warmup 3 --batch 131072 --max-time 1e6 --no-cpu --exact-step 0 --relaxed-step 0 --closed-step 0 --extras 0 --e2e-steps 1 --warmup-e2e 0"
-launch_table(os.path.join(G, "r2_launches_bench_small.csv"),
+launch_table(src("r2_launches_bench_small.csv"),
              "ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv python bench.py " + SMALL)
 P("Raw list: `r2_launches_bench_small.csv`.  As in round 1 this reduced configuration (131 072 slots, max_time 1e6) over-weights the rare "
   "wide bins when serialised: each of their launches lasts as long as its dependency chain however few trajectories it holds, while in "
   "the real run the ~20 kernels of a pass execute concurrently on separate streams.\n")
 P("## 2. Launch list of a full-size pool run (the bulk of a run: its first 9000 launches = ~460 passes)\n")
-launch_table(os.path.join(G, "r2_launches_pool.csv"),
+launch_table(src("r2_launches_pool.csv"),
              "N=2000000 MODE=fast ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv python scripts/pool_once.py")
 P("Raw list: `r2_launches_pool.csv`.  The same run without ncu: 12.6 s for 1047 passes (5.03e11 particle-steps/s with its drain): "
   "serialised, its first 460 passes alone take 28.5 s -- the kernels of a pass overlap more than two-fold.\n")
-metric_table(os.path.join(G, "r2_prof_pool_raw.csv"),
-             "3. The hot kernels at full occupancy, inside a pool run (`--set full`)",
-             "N=2000000 CAP=40000 ncu --set full --clock-control none --import-source on -k regex:'k_integrate_thread|k_free_flight|"
-             "k_pool_resolve|k_integrate_hybrid|k_integrate_smem' -s 17 -c 22 python scripts/pool_once.py   (2e6 trajectories of config C2 "
-             "in the pool, passes 2-3)")
+FULL = ("N=2000000 CAP=40000 ncu --set full --clock-control none --import-source on -k regex:'k_integrate_thread|k_free_flight|"
+        "k_pool_resolve|k_integrate_hybrid|k_integrate_smem' -s 17 -c 22 python scripts/pool_once.py   (2e6 trajectories of config C2 "
+        "in the pool, passes 2-3)")
+metric_table(src("r2_prof_pool_final_raw.csv"), "3. The hot kernels at full occupancy, inside a pool run (`--set full`), final register allocations", FULL)
+P("Raw: `r2_prof_pool_final_raw.csv`.  Captured on commit babdd72, where the step body was written inside `k_integrate_thread`; the "
+  "shipped build moves it into `integrate_thread_segment` (same arithmetic, same register allocations within 4, 2-5 % fewer "
+  "instructions per step -- the loop sizes in `r2_ptxas.md` are the shipped ones: A = 2: 128 instead of 135, A = 4: 322 instead of 333, "
+  "A = 8: 950 instead of 974); a 1e6-trajectory run takes 8.26-8.28 s with it against 8.29-8.46 s (`r2_forms.log`: inline form, segment form, twice).\n")
+metric_table(src("r2_prof_pool_raw.csv"),
+             "3b. The same capture of an intermediate build: the register finding (before)", FULL)
+P("Raw: `r2_prof_pool_raw.csv`.  This build differed from the one above in the text around the step loop only (time-slice bookkeeping "
+  "of a dropped experiment in the kernel's view structure): ptxas chose 96 / 128 / 168 registers for A = 3 / 4 / 6 where the final build has 112 / 146 / 228 "
+  "(`r2_ptxas.md`).  Compare the rows of the two tables at equal grid: the smaller allocations keep fewer gathers in flight "
+  "(long_scoreboard per instruction) and are slower although more warps are resident; the two-particle kernel is the opposite case "
+  "(72 registers by `__launch_bounds__`, 80 when ptxas is left alone) and its cap was kept.\n")
 P("## 4. The gather path: T-ref (6.4 MB, L1/L2-resident) against T-large (26.6 M entries = 106 MB)\n")
-gather_table([("T-ref", os.path.join(G, "r2_gather_pool_tlarge0.csv")), ("T-large", os.path.join(G, "r2_gather_pool_tlarge1.csv"))],
+gather_table([("T-ref", src("r2_gather_pool_tlarge0.csv")), ("T-large", src("r2_gather_pool_tlarge1.csv"))],
              "TLARGE={0,1} N=2000000 CAP=40000 ncu --kernel-name-base demangled --metrics gpu__time_duration.sum,smsp__inst_executed.sum,"
              "l1tex__t_{requests,sectors,bytes}_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sector_hit_rate.pct,lts__t_bytes.sum,"
              "lts__t_sector_hit_rate.pct,dram__bytes_{read,write}.sum,... -k regex:'k_integrate_thread<.int.[234],' -s 6 -c 6 "
              "python scripts/pool_once.py")
 P(open(os.path.join(PROF, "r2_reading.md")).read() if os.path.exists(os.path.join(PROF, "r2_reading.md")) else "")
 open(os.path.join(PROF, "r2_ncu_summary.md"), "w").write("\n".join(out) + "\n")
-for f in ("r2_launches_bench_small.csv", "r2_launches_pool.csv", "r2_prof_pool_raw.csv", "r2_gather_pool_tlarge0.csv", "r2_gather_pool_tlarge1.csv"):
-    shutil.copy(os.path.join(G, f), os.path.join(PROF, f))
+for f in ("r2_launches_bench_small.csv", "r2_launches_pool.csv", "r2_prof_pool_raw.csv", "r2_prof_pool_final_raw.csv",
+          "r2_gather_pool_tlarge0.csv", "r2_gather_pool_tlarge1.csv"):
+    if os.path.exists(os.path.join(G, f)):
+        shutil.copy(os.path.join(G, f), os.path.join(PROF, f))
 print("\n".join(out))

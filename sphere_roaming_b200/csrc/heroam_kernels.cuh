@@ -988,11 +988,128 @@ __device__ __forceinline__ void rebuild_forces(const DevView &v, const float (&r
 // (all of it drain) takes 4.2 s with it, 4.65 s without, 5.1 s with the one-step look-ahead
 // into registers it replaced (DESIGN.md section 7 has the other variants).
 // ---------------------------------------------------------------------------------
+// One segment of a trajectory with A moving particles, by one thread: loads the records, runs
+// steps [m.steps, m.step_stop) or up to a meeting, leaves the records (clean, or mid-step) and
+// updates m (steps, clock, status).  Returns the number of steps completed.
+template <int A, class P, bool LOOKAHEAD>
+__device__ __forceinline__ uint32_t integrate_thread_segment(const DevView &v, TrajMeta &m, const unsigned sink_addr,
+                                                             unsigned long long &inrange_total) {
+  const Consts &c = v.c;
+  heroam_particle *rec[A];
+  float q[A][4], w[A][3], r[A][3], f[A][3], hk[A][3], wh[A][3], r_old[A][3];
+#pragma unroll
+  for (int s = 0; s < A; ++s) {
+    rec[s] = v.particles + m.first + v.act[m.first + s];
+    const heroam_particle *p = rec[s];
+    q[s][0] = p->orientation[0]; q[s][1] = p->orientation[1];
+    q[s][2] = p->orientation[2]; q[s][3] = p->orientation[3];
+    ld3(p->position, r[s]);
+    load_w<P>(c, p->ang_velocity, w[s]);
+    load_f<P>(c, p->force, f[s]);
+  }
+  if (P::turbo) rebuild_forces<A, P>(v, r, f);
+#pragma unroll
+  for (int s = 0; s < A; ++s) half_kick<P>(c, r[s], f[s], hk[s]);
+  uint32_t steps = m.steps;
+  float time = m.time;
+  bool met = false;
+  constexpr int NP = A * (A - 1) / 2;
+  float pos_prev[LOOKAHEAD ? NP + 1 : 1];
+#pragma unroll
+  for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
+  while (steps < m.step_stop) {
+    const bool rn = renorm_at<P>(steps);
+    // first half kick + drift (simulation.c:478-490)
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      r_old[s][0] = r[s][0]; r_old[s][1] = r[s][1]; r_old[s][2] = r[s][2];
+      wh[s][0] = P::add(w[s][0], hk[s][0]);
+      wh[s][1] = P::add(w[s][1], hk[s][1]);
+      wh[s][2] = P::add(w[s][2], hk[s][2]);
+      advance_orientation<P>(c, wh[s], q[s], P::renorm_every == 1u);
+    }
+    if (P::renorm_every > 1u && rn) {  // one branch per step for all particles; uniform when the warp is in phase
+#pragma unroll
+      for (int s = 0; s < A; ++s) renormalise(q[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      pole_position<P>(c, q[s], r[s]);
+      f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
+    }
+    // all pairs in the reference's (j,k) order (:178-233)
+    // Branch-free and staged row by row: geometry and gathers of a whole row are
+    // issued before any of them is consumed.
+    float dmin = 3.0e38f;
+    uint32_t in_step = 0;
+#pragma unroll
+    for (int j = 0; j < A - 1; ++j) {
+      PairGeom g[A];
+      float tv[A];
+#pragma unroll
+      for (int k = j + 1; k < A; ++k) {
+        g[k] = pair_geom<P>(c, r[j], r[k]);
+        tv[k] = pair_gather<P>(v, g[k]);
+        if (LOOKAHEAD) {
+          // L1 prefetch by cp.async: the sector around the table position predicted for two steps
+          // from now is copied to a dummy slot of shared memory that nobody reads; the copy passes
+          // through L1, so the ordinary gather of that step finds its sector there
+          const int pi = j * A - j * (j + 1) / 2 + (k - j - 1);  // index of pair (j,k), static after unrolling
+          const float pos = P::turbo ? fmaf(g[k].d, c.inv_grid, c.pos_bias) : __fmul_rn(__fsub_rn(g[k].d, c.grid_start), c.inv_grid);
+          const float guess = fmaf(3.0f, pos, -2.0f * pos_prev[pi]);
+          pos_prev[pi] = pos;
+          const unsigned at = min((unsigned)__float2int_rz(guess), (unsigned)c.grid_len);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink_addr), "l"((P::turbo ? v.table_k : v.table) + at));
+        }
+        dmin = fminf(dmin, g[k].d);
+        if (P::count) in_step += g[k].inside ? 1u : 0u;
+      }
+#pragma unroll
+      for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
+    }
+    if (LOOKAHEAD) {
+      asm volatile("cp.async.commit_group;");
+      asm volatile("cp.async.wait_group 3;");
+    }
+    if (dmin < c.icd2) { met = true; break; }
+    // second half kick (:496-509); velocity and clock fields are written at the end
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      half_kick<P>(c, r[s], f[s], hk[s]);
+      w[s][0] = P::add(wh[s][0], hk[s][0]);
+      w[s][1] = P::add(wh[s][1], hk[s][1]);
+      w[s][2] = P::add(wh[s][2], hk[s][2]);
+    }
+    time = __fadd_rn(time, c.dt);
+    ++steps;
+    inrange_total += in_step;
+  }
+  if (LOOKAHEAD) asm volatile("cp.async.wait_all;");
+  const uint32_t done_steps = steps - m.steps;
+  if (met) {
+#pragma unroll
+    for (int s = 0; s < A; ++s) write_midstep<P>(c, rec[s], q[s], r[s], w[s], wh[s], r_old[s], time, steps > 0);
+    m.status = ST_MIDSTEP;
+  } else if (done_steps > 0) {
+#pragma unroll
+    for (int s = 0; s < A; ++s) {
+      const uint32_t j = (uint32_t)(rec[s] - (v.particles + m.first));
+      write_clean<P>(c, rec[s], q[s], r[s], w[s], f[s], time, j + 1u < m.no);
+    }
+  }
+  m.steps = steps;
+  m.time = time;
+  return done_steps;
+}
+
 // Registers: ptxas left to itself takes 80 for A = 2; capped at 72 (seven blocks per SM instead of six) the
 // two-particle kernel is 15 % faster at full occupancy (ncu, round 2: 4.35 against 5.14 ms for 3.8 k blocks).
 // The wider ones lose from a cap: with fewer registers fewer gathers are in flight (A = 3, 4, 6 at
-// 96 / 128 / 168 registers instead of 108 / 140 / 214: 6-60 % slower, long_scoreboard 2.3-2.9 cycles per
-// instruction instead of 0.4-1.3).
+// 96 / 128 / 168 registers instead of 108 / 144 / 228: 6-60 % slower, long_scoreboard 2.3-2.9 cycles per
+// instruction instead of 0.4-1.3; profiles/r2_ncu_summary.md sections 3 and 3b).
+// The body lives in integrate_thread_segment rather than in the kernel itself: same arithmetic, but ptxas
+// then carries r_old without half of the register copies (loop of A = 2: 128 instead of 135 instructions
+// and no spill under the 72-register cap; A = 6: 595 instead of 613; A = 8: 950 instead of 974).
 template <int A, class P, bool LOOKAHEAD = false>
 __global__ void __launch_bounds__(INTEGRATE_TPB, (A == 2 && !LOOKAHEAD) ? 7 : 1)
 k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count) {
@@ -1001,113 +1118,9 @@ k_integrate_thread(DevView v, const uint32_t *__restrict__ list, uint32_t count)
   const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long done_steps = 0, inrange_total = 0;
   if (item < count) {
-    const Consts &c = v.c;
     const uint32_t t = list[item];
     TrajMeta m = v.meta[t];
-    heroam_particle *rec[A];
-    float q[A][4], w[A][3], r[A][3], f[A][3], hk[A][3], wh[A][3], r_old[A][3];
-#pragma unroll
-    for (int s = 0; s < A; ++s) {
-      rec[s] = v.particles + m.first + v.act[m.first + s];
-      const heroam_particle *p = rec[s];
-      q[s][0] = p->orientation[0]; q[s][1] = p->orientation[1];
-      q[s][2] = p->orientation[2]; q[s][3] = p->orientation[3];
-      ld3(p->position, r[s]);
-      load_w<P>(c, p->ang_velocity, w[s]);
-      load_f<P>(c, p->force, f[s]);
-    }
-    if (P::turbo) rebuild_forces<A, P>(v, r, f);
-#pragma unroll
-    for (int s = 0; s < A; ++s) half_kick<P>(c, r[s], f[s], hk[s]);
-    uint32_t steps = m.steps;
-    float time = m.time;
-    bool met = false;
-    constexpr int NP = A * (A - 1) / 2;
-    float pos_prev[LOOKAHEAD ? NP + 1 : 1];
-#pragma unroll
-    for (int i = 0; i < (LOOKAHEAD ? NP : 0); ++i) pos_prev[i] = 0.0f;
-    while (steps < m.step_stop) {
-      const bool rn = renorm_at<P>(steps);
-      // first half kick + drift (simulation.c:478-490)
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        r_old[s][0] = r[s][0]; r_old[s][1] = r[s][1]; r_old[s][2] = r[s][2];
-        wh[s][0] = P::add(w[s][0], hk[s][0]);
-        wh[s][1] = P::add(w[s][1], hk[s][1]);
-        wh[s][2] = P::add(w[s][2], hk[s][2]);
-        advance_orientation<P>(c, wh[s], q[s], P::renorm_every == 1u);
-      }
-      if (P::renorm_every > 1u && rn) {  // one branch per step for all particles; uniform when the warp is in phase
-#pragma unroll
-        for (int s = 0; s < A; ++s) renormalise(q[s]);
-      }
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        pole_position<P>(c, q[s], r[s]);
-        f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = 0.0f;
-      }
-      // all pairs in the reference's (j,k) order (:178-233)
-      // Branch-free and staged row by row: geometry and gathers of a whole row are
-      // issued before any of them is consumed.
-      float dmin = 3.0e38f;
-      uint32_t in_step = 0;
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) {
-        PairGeom g[A];
-        float tv[A];
-#pragma unroll
-        for (int k = j + 1; k < A; ++k) {
-          g[k] = pair_geom<P>(c, r[j], r[k]);
-          tv[k] = pair_gather<P>(v, g[k]);
-          if (LOOKAHEAD) {
-            // L1 prefetch by cp.async: the sector around the table position predicted for two steps
-            // from now is copied to a dummy slot of shared memory that nobody reads; the copy passes
-            // through L1, so the ordinary gather of that step finds its sector there
-            const int pi = j * A - j * (j + 1) / 2 + (k - j - 1);  // index of pair (j,k), static after unrolling
-            const float pos = P::turbo ? fmaf(g[k].d, c.inv_grid, c.pos_bias) : __fmul_rn(__fsub_rn(g[k].d, c.grid_start), c.inv_grid);
-            const float guess = fmaf(3.0f, pos, -2.0f * pos_prev[pi]);
-            pos_prev[pi] = pos;
-            const unsigned at = min((unsigned)__float2int_rz(guess), (unsigned)c.grid_len);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sink_addr), "l"((P::turbo ? v.table_k : v.table) + at));
-          }
-          dmin = fminf(dmin, g[k].d);
-          if (P::count) in_step += g[k].inside ? 1u : 0u;
-        }
-#pragma unroll
-        for (int k = j + 1; k < A; ++k) pair_apply<P>(pair_scale<P>(tv[k], g[k].d), g[k], f[j], f[k]);
-      }
-      if (LOOKAHEAD) {
-        asm volatile("cp.async.commit_group;");
-        asm volatile("cp.async.wait_group 3;");
-      }
-      if (dmin < c.icd2) { met = true; break; }
-      // second half kick (:496-509); velocity and clock fields are written at the end
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        half_kick<P>(c, r[s], f[s], hk[s]);
-        w[s][0] = P::add(wh[s][0], hk[s][0]);
-        w[s][1] = P::add(wh[s][1], hk[s][1]);
-        w[s][2] = P::add(wh[s][2], hk[s][2]);
-      }
-      time = __fadd_rn(time, c.dt);
-      ++steps;
-      inrange_total += in_step;
-    }
-    if (LOOKAHEAD) asm volatile("cp.async.wait_all;");
-    done_steps = steps - m.steps;
-    if (met) {
-#pragma unroll
-      for (int s = 0; s < A; ++s) write_midstep<P>(c, rec[s], q[s], r[s], w[s], wh[s], r_old[s], time, steps > 0);
-      m.status = ST_MIDSTEP;
-    } else if (done_steps > 0) {
-#pragma unroll
-      for (int s = 0; s < A; ++s) {
-        const uint32_t j = (uint32_t)(rec[s] - (v.particles + m.first));
-        write_clean<P>(c, rec[s], q[s], r[s], w[s], f[s], time, j + 1u < m.no);
-      }
-    }
-    m.steps = steps;
-    m.time = time;
+    done_steps = integrate_thread_segment<A, P, LOOKAHEAD>(v, m, sink_addr, inrange_total);
     v.meta[t] = m;
   }
   const unsigned long long ds = warp_sum_u64(done_steps);
