@@ -38,6 +38,17 @@ def shard_sweep(points, rank: int, world: int):
     return out
 
 
+def shard_size_sweep(points, rank: int, world: int):
+    """A rank's share of a droplet-size sweep (reference main.c:158-164; Engine.run_size_sweep):
+    every point (he_number, count, first_index) keeps its place and its size, its trajectories
+    are split by index like a single run's (host/heroam_main.c stats_for_sweep does the same per GPU)."""
+    out = []
+    for he_number, count, first_index in points:
+        first, n = shard_range(count, rank, world)
+        out.append((he_number, n, first_index + first))
+    return out
+
+
 def stats_from_records(counts: np.ndarray, flat: np.ndarray, results: np.ndarray, max_time: float) -> dict:
     """Host-side equivalent of the device histogram kernel (k_stats), for batches whose
     final records were brought back to the host (the drop-in simulate path)."""

@@ -27,6 +27,20 @@ def test_shard_range_partitions_exactly():
         shard_range(10, 2, 2)
 
 
+def test_shard_size_sweep_partitions_every_point():
+    from sphere_roaming_b200.sharding import shard_size_sweep
+
+    points = [(6000, 2500, 0), (10000, 3000, 50), (16000, 7, 7), (30000, 0, 123456789012)]
+    for world in (1, 2, 3, 8):
+        shards = [shard_size_sweep(points, r, world) for r in range(world)]
+        for p, (he, count, first) in enumerate(points):
+            at = first
+            for s in shards:
+                assert s[p][0] == he and s[p][2] == at  # contiguous, in rank order, size unchanged
+                at += s[p][1]
+            assert at == first + count
+
+
 def _local_stats(first, count, total_conf_number, max_time):
     from oracle.binding import PortOracle
     from sphere_roaming_b200.forcetable import synthetic_table
